@@ -1,0 +1,122 @@
+/*
+ * smap_b200 - C ABI of the B200-native SMAP inference hot path.
+ *
+ * Plain C: opaque handle, raw pointers, sizes, int error codes (0 = ok, < 0 = error; the text is
+ * available from smapb_last_error()).  Nothing throws across this boundary, no torch types appear in
+ * it.  All *_dev pointers are device pointers on the handle's device, caller-owned; the handle owns
+ * its workspace (no per-call cudaMalloc).  Calls are stream-ordered on `stream` (a cudaStream_t passed
+ * as void*; NULL = legacy default stream) and do NOT synchronise unless stated.
+ *
+ * Each entry point names the reference interface it replaces (paths relative to zju3dv/SMAP).
+ */
+#ifndef SMAP_B200_H
+#define SMAP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct smapb_handle smapb_handle;
+
+#define SMAPB_NJ 15        /* key points,            extensions/association.cpp:18 */
+#define SMAPB_NL 14        /* limbs,                 extensions/association.cpp:19 */
+#define SMAPB_MAXP 127     /* max peaks per channel, extensions/association.cpp:20 */
+#define SMAPB_NC2D 43      /* 2D head channels,      model/smap.py:320 */
+#define SMAPB_SCALE_LEN 9  /* scale,img_w,img_h,net_w,net_h,f_x,f_y,cx,cy (exps/stage3_root2/test.py:99-103) */
+
+/* precision of the tensor-core convolutions */
+#define SMAPB_PREC_BF16X3 3 /* split-bf16 (hi+lo) operands, 3 MMAs per product, fp32 accumulate: fp32-faithful */
+#define SMAPB_PREC_BF16 1   /* single bf16 operands (fast, ~1e-2 relative; NOT parity grade) */
+
+/* ---- lifetime -------------------------------------------------------------------------------- */
+/* Replaces: per-call ArrayGpu<T> scratch (extensions/arraygpu.hpp:62-77, re-created on every
+ * extract(), extensions/association.cpp:47-63) and SMAP(cfg).to('cuda') (exps/stage3_root2/test.py:190-192).
+ * in_h/in_w: network input size (multiples of 32); heat-maps are in_h/4 x in_w/4. */
+int smapb_create(smapb_handle** out, int device, int max_batch, int in_h, int in_w);
+void smapb_destroy(smapb_handle* h);
+const char* smapb_last_error(const smapb_handle* h); /* never NULL; h may be NULL for create errors */
+int smapb_version(void);
+
+/* ---- weights (model/smap.py state-dict schema, 268 conv_bn_relu units x 7 tensors) ------------ */
+/* Replaces: model.load_state_dict(sd) (exps/stage3_root2/test.py:210-212).  `key` is the reference
+ * key ("stage0.downsample.layer1.0.conv_bn_relu1.conv.weight", "top.conv.bn.running_var", ...),
+ * `host` fp32 host data, copied.  num_batches_tracked keys are accepted and ignored. */
+int smapb_load_weight(smapb_handle* h, const char* key, const float* host, const int64_t* shape, int ndim);
+/* BN folding (model/smap.py:23, eps 1e-5), NHWC/K-major repack, hi/lo split, TMA descriptors,
+ * execution plan.  precision: SMAPB_PREC_*.  Must be called once after all weights are loaded. */
+int smapb_finalize_weights(smapb_handle* h, int precision);
+
+/* ---- backbone -------------------------------------------------------------------------------- */
+/* Replaces: SMAP.forward inference branch (model/smap.py:403-419).
+ * imgs_nchw_dev: fp32 [B,3,in_h,in_w] (normalised BGR).  Outputs fp32 NCHW:
+ * hm2d [B,43,h,w], detd [B,14,h,w], rootd [B,1,h,w] with h=in_h/4, w=in_w/4. */
+int smapb_backbone_forward(smapb_handle* h, const float* imgs_nchw_dev, int B, float* hm2d_dev, float* detd_dev,
+                           float* rootd_dev, void* stream);
+/* Flip-TTA merge (exps/stage3_root2/test.py:55-70) and the per-image rescale hms[:15]/=255,
+ * hms[15:]/=127 (exps/stage3_root2/test.py:111-112), in place on hm2d [B,43,h,w].
+ * hm2d_flip_dev may be NULL (no TTA).  do_scale != 0 applies the division. */
+int smapb_merge_scale(smapb_handle* h, float* hm2d_dev, const float* hm2d_flip_dev, int B, int do_scale,
+                      void* stream);
+
+/* ---- association ----------------------------------------------------------------------------- */
+/* Replaces: dapalib.extract (extensions/association.cpp:34-120): nmsGpu + connectBodyPartsGpu.
+ * hms_dev: fp32 [B,43,h,w] already divided by 255/127.
+ * peaks_dev: fp32 [B,15,128,3]  slot 0 = (count,0,0), slots 1..count = (x,y,score) in raster order,
+ *            remaining slots zero (the reference leaves them uninitialised).
+ * pair_scores_dev: fp32 [B,14,127,127], -1 outside nA x nB exactly as pafScoreKernel writes. */
+int smapb_assoc_extract(smapb_handle* h, const float* hms_dev, int B, float* peaks_dev, float* pair_scores_dev,
+                        void* stream);
+/* Replaces: dapalib.connect / findConnectedJoints (extensions/association.cpp:123-233).
+ * rdepth_dev: fp32 [B,h,w].  bodies_dev: fp32 [B,127,15,4] = (x,y,0,score) in heat-map pixels, rows in
+ * ascending root depth, rows >= counts[b] zero.  counts_dev: int32 [B]. */
+int smapb_assoc_connect(smapb_handle* h, const float* hms_dev, const float* rdepth_dev, int B, int root_idx,
+                        int dist_flag, float* bodies_dev, int* counts_dev, void* stream);
+
+/* ---- 3D lift ---------------------------------------------------------------------------------- */
+/* Replaces: x4 stride + nearest upsample + register_pred(no GT) + generate_relZ + gen_3d_pose
+ * (exps/stage3_root2/test.py:117-134, test_util.py:18-99, lib/utils/post_3d.py:4-27).
+ * scales_dev: float64 [B,9] (SMAPB_SCALE_LEN).  Outputs (fixed stride, tails zeroed):
+ * pred2d fp32 [B,127,15,4] (x,y in net-input pixels, root-relative z, score),
+ * pred3d fp64 [B,127,15,4] (X,Y,Z,score), root_depth fp64 [B,127], counts_out int32 [B]. */
+int smapb_lift3d(smapb_handle* h, const float* bodies_dev, const int* counts_dev, const float* detd_dev,
+                 const float* rootd_dev, const double* scales_dev, int B, float* pred2d_dev, double* pred3d_dev,
+                 double* root_depth_dev, int* counts_out_dev, void* stream);
+
+/* ---- whole path -------------------------------------------------------------------------------- */
+/* Byte layout of one per-image skeleton record (the all-gather payload). */
+typedef struct smapb_record {
+    double pred3d[SMAPB_MAXP][SMAPB_NJ][4];
+    double root_depth[SMAPB_MAXP];
+    float pred2d[SMAPB_MAXP][SMAPB_NJ][4];
+    int32_t count;
+    int32_t pad_;
+} smapb_record;
+
+/* Replaces: the per-batch body of generate_3d_point_pairs (exps/stage3_root2/test.py:48-134) with
+ * device-resident input: forward (+ flipped forward when do_flip) -> merge/scale -> connect -> lift.
+ * records_dev: smapb_record[B]. */
+int smapb_infer_device(smapb_handle* h, const float* imgs_nchw_dev, const double* scales_dev, int B, int do_flip,
+                       smapb_record* records_dev, void* stream);
+/* Same with HOST buffers (pinned or pageable): H2D of imgs/scales, infer, D2H of records, then
+ * synchronises `stream`.  This is the call bench.py times as `e2e`. */
+int smapb_infer_host(smapb_handle* h, const float* imgs_nchw_host, const double* scales_host, int B, int do_flip,
+                     smapb_record* records_host, void* stream);
+
+/* ---- introspection ----------------------------------------------------------------------------- */
+/* number of kernels launched by this handle since creation */
+int64_t smapb_launch_count(const smapb_handle* h);
+/* conv plan: number of tensor-core conv launches per forward and their algorithmic FLOPs (2*MACs, 1x) */
+int smapb_plan_info(const smapb_handle* h, int B, int* n_conv_launches, double* conv_flops);
+/* Run one standalone convolution through the tensor-core path (test/bench hook).
+ * x: fp32 NHWC [B,H,W,Cin]; w: fp32 [Cout,Cin,k,k]; bias fp32 [Cout]; res (optional) fp32 NHWC of the
+ * output shape added before the ReLU; y: fp32 NHWC [B,Ho,Wo,Cout].  All device pointers. */
+int smapb_conv_test(smapb_handle* h, const float* x_dev, const float* w_dev, const float* bias_dev,
+                    const float* res_dev, int B, int H, int W, int Cin, int Cout, int k, int stride, int relu,
+                    int precision, float* y_dev, float* ms_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SMAP_B200_H */

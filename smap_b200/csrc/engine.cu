@@ -1,0 +1,1044 @@
+// Host side of libsmap_b200: handle, weight folding/repack, execution plan, C ABI (include/smap_b200.h).
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/smap_b200.h"
+#include "assoc.h"
+#include "conv_tc.cuh"
+#include "elementwise.h"
+
+using namespace smapb;
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// small utilities
+// ------------------------------------------------------------------------------------------------
+thread_local std::string g_create_error = "";
+
+inline uint16_t f32_to_bf16_rn(float f) {
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);  // NaN
+    const uint32_t lsb = (u >> 16) & 1u;
+    u += 0x7fffu + lsb;
+    return (uint16_t)(u >> 16);
+}
+inline float bf16_to_f32(uint16_t b) {
+    uint32_t u = (uint32_t)b << 16;
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// split-bf16 NHWC activation tensor: plane 0 = hi, plane 1 = lo
+struct Act {
+    __nv_bfloat16* ptr = nullptr;
+    int N = 0, H = 0, W = 0, C = 0;
+    long long plane() const { return (long long)N * H * W * C; }
+};
+struct ActF32 {
+    float* ptr = nullptr;
+    int N = 0, H = 0, W = 0, C = 0;
+};
+
+struct ConvLayer {
+    std::string name;
+    int Cin = 0, Cout = 0, Cout_pad = 0, k = 1, stride = 1, pad = 0, relu = 0;
+    __nv_bfloat16* w_dev = nullptr;  // [T][taps][Cout_pad][Cin]
+    float* bias_dev = nullptr;       // [Cout_pad]
+};
+
+enum OpKind { OP_STEM, OP_MAXPOOL, OP_CONV, OP_UPADD, OP_HEADMERGE };
+struct Op {
+    OpKind kind;
+    // conv
+    ConvParams cp;
+    int block_n = 0;
+    double flops = 0;
+    // generic tensors
+    Act a, b, out;
+    ActF32 f4, f3, f2;
+    int cout = 0;  // head merge real channel count
+    int which_out = 0;  // 0 hm2d, 1 detd, 2 rootd
+};
+
+struct Plan {
+    int B = 0;
+    std::vector<Op> ops;
+    std::vector<void*> allocs;
+    int n_conv = 0;
+    double conv_flops = 0;
+    cudaGraphExec_t graph = nullptr;
+};
+
+}  // namespace
+
+struct smapb_handle {
+    int device = 0, max_batch = 0, in_h = 0, in_w = 0, h = 0, w = 0;
+    int sm_count = 148;
+    std::string err;
+    int64_t launches = 0;
+    // weights
+    std::map<std::string, std::vector<float>> raw;
+    std::map<std::string, std::vector<int64_t>> raw_shape;
+    std::map<std::string, ConvLayer> layers;
+    float* stem_w = nullptr;  // [147][64]
+    float* stem_b = nullptr;
+    int nterms = 3;  // MMA terms (3 = bf16x3, 1 = bf16)
+    int planes = 2;  // activation planes (2 or 1)
+    bool finalized = false;
+    std::map<int, std::unique_ptr<Plan>> plans;
+    // association workspace (sized for max_batch)
+    float* peaks = nullptr;
+    float* scores = nullptr;
+    float* bodies = nullptr;
+    int* counts = nullptr;
+    // whole-path workspace
+    float* imgs_dev = nullptr;
+    float* imgs_flip = nullptr;
+    float* hm = nullptr;
+    float* hm_flip = nullptr;
+    float* detd = nullptr;
+    float* rootd = nullptr;
+    float* scratch_detd = nullptr;
+    float* scratch_rootd = nullptr;
+    double* scales_dev = nullptr;
+    smapb_record* records_dev = nullptr;
+    bool use_graph = true;
+};
+
+namespace {
+
+int fail(smapb_handle* h, int code, const std::string& msg) {
+    if (h) h->err = msg;
+    return code;
+}
+#define CK(call)                                                                                          \
+    do {                                                                                                  \
+        cudaError_t e_ = (call);                                                                          \
+        if (e_ != cudaSuccess)                                                                            \
+            return fail(h, -10, std::string(#call) + ": " + cudaGetErrorString(e_) + " @" + std::to_string(__LINE__)); \
+    } while (0)
+
+template <typename T>
+int dev_alloc(smapb_handle* h, T** p, size_t count) {
+    CK(cudaMalloc((void**)p, count * sizeof(T)));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// tensor maps
+// ------------------------------------------------------------------------------------------------
+int make_act_map(smapb_handle* h, CUtensorMap* m, const __nv_bfloat16* ptr, long long C, long long W, long long H,
+                 long long N, int T, long long plane_elems, int box_w, int box_h, int stride) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return fail(h, -20, "cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N, (cuuint64_t)T};
+    cuuint64_t strides[4] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2,
+                             (cuuint64_t)plane_elems * 2};
+    cuuint32_t box[5] = {64, (cuuint32_t)box_w, (cuuint32_t)box_h, 1, 1};
+    cuuint32_t es[5] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, (void*)ptr, dims, strides, box, es,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        char buf[256];
+        snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled(act) failed: %d  dims=(%lld,%lld,%lld,%lld,%d) box=(64,%d,%d) s=%d",
+                 (int)r, C, W, H, N, T, box_w, box_h, stride);
+        return fail(h, -21, buf);
+    }
+    return 0;
+}
+int make_w_map(smapb_handle* h, CUtensorMap* m, const __nv_bfloat16* ptr, int Cin, int Cout_pad, int taps, int T,
+               int block_n) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return fail(h, -20, "cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)Cout_pad, (cuuint64_t)taps, (cuuint64_t)T};
+    cuuint64_t strides[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)Cout_pad * Cin * 2, (cuuint64_t)taps * Cout_pad * Cin * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)block_n, 1, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)ptr, dims, strides, box, es,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(h, -21, "cuTensorMapEncodeTiled(weights) failed: " + std::to_string((int)r));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// conv launch
+// ------------------------------------------------------------------------------------------------
+template <int BN, int NT>
+cudaError_t launch_conv_inst(const ConvParams& cp, int grid, cudaStream_t st, bool pdl) {
+    using Cfg = ConvCfg<BN, NT>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e =
+            cudaFuncSetAttribute(conv_tc_kernel<BN, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(256);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, NT>, cp);
+}
+cudaError_t launch_conv(const ConvParams& cp, int block_n, int nterms, int sm_count, cudaStream_t st, bool pdl) {
+    const int grid = cp.total_tiles < sm_count ? cp.total_tiles : sm_count;
+#define SMAPB_CASE(BN)                                                              \
+    case BN:                                                                        \
+        return nterms == 3 ? launch_conv_inst<BN, 3>(cp, grid, st, pdl) : launch_conv_inst<BN, 1>(cp, grid, st, pdl);
+    switch (block_n) {
+        SMAPB_CASE(256)
+        SMAPB_CASE(128)
+        SMAPB_CASE(64)
+        SMAPB_CASE(32)
+    }
+#undef SMAPB_CASE
+    return cudaErrorInvalidValue;
+}
+
+// Fill a ConvParams for `layer` applied to `in`, producing (out | out_f32).
+int setup_conv(smapb_handle* h, const ConvLayer& L, const Act& in, const Act* res, const Act* post1, const Act* post2,
+               const Act* out, const ActF32* outf, int relu, ConvParams* cp, int* block_n_out, double* flops_out) {
+    const int Ho = (in.H + 2 * L.pad - L.k) / L.stride + 1, Wo = (in.W + 2 * L.pad - L.k) / L.stride + 1;
+    const int N = in.N;
+    if (in.C != L.Cin) return fail(h, -30, "conv " + L.name + ": Cin mismatch");
+    if (L.Cin % 64 != 0) return fail(h, -30, "conv " + L.name + ": Cin must be a multiple of 64");
+    memset(cp, 0, sizeof(*cp));
+    const bool flat = (L.k == 1 && L.stride == 1);
+    int tw, th, tiles_x, tiles_y, nimg;
+    int rc;
+    if (flat) {
+        tw = 128;
+        th = 1;
+        const long long M = (long long)N * Ho * Wo;
+        tiles_x = (int)((M + 127) / 128);
+        tiles_y = 1;
+        nimg = 1;
+        cp->Hout = 1;
+        cp->Wout = (int)M;
+        rc = make_act_map(h, &cp->tmA, in.ptr, in.C, M, 1, 1, h->planes, in.plane(), 128, 1, 1);
+    } else {
+        // pick the patch shape with the fewest wasted rows
+        double best = -1;
+        tw = 16;
+        for (int c = 128; c >= 1; c >>= 1) {
+            const int t_h = 128 / c;
+            if (c * L.stride > 256 || t_h * L.stride > 256) continue;
+            const double util = ((double)Wo * Ho) / ((double)((Wo + c - 1) / c) * c * ((Ho + t_h - 1) / t_h) * t_h);
+            if (util > best + 1e-9) {
+                best = util;
+                tw = c;
+            }
+        }
+        th = 128 / tw;
+        tiles_x = (Wo + tw - 1) / tw;
+        tiles_y = (Ho + th - 1) / th;
+        nimg = N;
+        cp->Hout = Ho;
+        cp->Wout = Wo;
+        rc = make_act_map(h, &cp->tmA, in.ptr, in.C, in.W, in.H, N, h->planes, in.plane(), tw * L.stride,
+                          th * L.stride, L.stride);
+    }
+    if (rc) return rc;
+    int twl = 0;
+    while ((1 << twl) < tw) twl++;
+    cp->Nimg = nimg;
+    cp->tw_log2 = twl;
+    cp->th = th;
+    cp->tiles_x = tiles_x;
+    cp->tiles_y = tiles_y;
+    const long long m_tiles = (long long)tiles_x * tiles_y * nimg;
+    // BLOCK_N: the largest tile that still yields at least one full wave of CTAs, else the smallest >= 64
+    int bn = 0;
+    const int cands[4] = {256, 128, 64, 32};
+    for (int c : cands) {
+        if (L.Cout_pad % c) continue;
+        if (m_tiles * (L.Cout_pad / c) >= h->sm_count) {
+            bn = c;
+            break;
+        }
+    }
+    if (!bn) {
+        for (int c : {64, 128, 256, 32})
+            if (L.Cout_pad % c == 0) {
+                bn = c;
+                break;
+            }
+    }
+    cp->Cout = L.Cout_pad;
+    cp->ksize = L.k;
+    cp->stride = L.stride;
+    cp->pad = L.pad;
+    cp->kchunks = L.Cin / 64;
+    cp->n_tiles = L.Cout_pad / bn;
+    cp->total_tiles = (int)(m_tiles * cp->n_tiles);
+    cp->bias = L.bias_dev;
+    cp->res = res ? res->ptr : nullptr;
+    cp->post1 = post1 ? post1->ptr : nullptr;
+    cp->post2 = post2 ? post2->ptr : nullptr;
+    cp->out = out ? out->ptr : nullptr;
+    cp->out_f32 = outf ? outf->ptr : nullptr;
+    cp->plane_stride = (long long)N * Ho * Wo * L.Cout_pad;
+    cp->relu = relu;
+    rc = make_w_map(h, &cp->tmB, L.w_dev, L.Cin, L.Cout_pad, L.k * L.k, h->planes, bn);
+    if (rc) return rc;
+    *block_n_out = bn;
+    if (flops_out) *flops_out = 2.0 * N * Ho * Wo * (double)L.Cout * L.Cin * L.k * L.k;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// weights: fold BN, repack, upload
+// ------------------------------------------------------------------------------------------------
+int fold_unit(smapb_handle* h, const std::string& name, std::vector<float>* wf, std::vector<float>* bf, int* Cout,
+              int* Cin, int* k) {
+    auto need = [&](const char* suffix) -> const std::vector<float>* {
+        auto it = h->raw.find(name + suffix);
+        return it == h->raw.end() ? nullptr : &it->second;
+    };
+    const auto* w = need(".conv.weight");
+    const auto* b = need(".conv.bias");
+    const auto* g = need(".bn.weight");
+    const auto* beta = need(".bn.bias");
+    const auto* mu = need(".bn.running_mean");
+    const auto* var = need(".bn.running_var");
+    if (!w || !b || !g || !beta || !mu || !var) return fail(h, -40, "missing weights for unit " + name);
+    const auto& shp = h->raw_shape[name + ".conv.weight"];
+    if (shp.size() != 4) return fail(h, -40, "bad weight rank for " + name);
+    *Cout = (int)shp[0];
+    *Cin = (int)shp[1];
+    *k = (int)shp[2];
+    const size_t per = (size_t)(*Cin) * (*k) * (*k);
+    wf->resize(w->size());
+    bf->resize(*Cout);
+    for (int co = 0; co < *Cout; co++) {
+        // BN eval (model/smap.py:23): y = (x - mean) / sqrt(var + 1e-5) * gamma + beta
+        const double s = (double)(*g)[co] / sqrt((double)(*var)[co] + 1e-5);
+        for (size_t i = 0; i < per; i++) (*wf)[co * per + i] = (float)((double)(*w)[co * per + i] * s);
+        (*bf)[co] = (float)(((double)(*b)[co] - (double)(*mu)[co]) * s + (double)(*beta)[co]);
+    }
+    return 0;
+}
+
+int upload_conv_layer(smapb_handle* h, ConvLayer& L, const std::vector<float>& wf, const std::vector<float>& bf) {
+    const int taps = L.k * L.k;
+    const size_t plane = (size_t)taps * L.Cout_pad * L.Cin;
+    std::vector<uint16_t> host(plane * h->planes, 0);
+    for (int co = 0; co < L.Cout; co++)
+        for (int ci = 0; ci < L.Cin; ci++)
+            for (int t = 0; t < taps; t++) {
+                const float v = wf[((size_t)co * L.Cin + ci) * taps + t];
+                const uint16_t hi = f32_to_bf16_rn(v);
+                const size_t o = ((size_t)t * L.Cout_pad + co) * L.Cin + ci;
+                host[o] = hi;
+                if (h->planes == 2) host[plane + o] = f32_to_bf16_rn(v - bf16_to_f32(hi));
+            }
+    std::vector<float> bias(L.Cout_pad, 0.f);
+    for (int co = 0; co < L.Cout; co++) bias[co] = bf[co];
+    if (!L.w_dev) {
+        if (dev_alloc(h, &L.w_dev, host.size())) return -10;
+        if (dev_alloc(h, &L.bias_dev, bias.size())) return -10;
+    }
+    CK(cudaMemcpy(L.w_dev, host.data(), host.size() * 2, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(L.bias_dev, bias.data(), bias.size() * 4, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+int pad32(int c) { return (c + 31) / 32 * 32; }
+
+// ------------------------------------------------------------------------------------------------
+// plan
+// ------------------------------------------------------------------------------------------------
+struct PlanBuilder {
+    smapb_handle* h;
+    Plan* plan;
+    int B;
+    int rc = 0;
+
+    Act new_act(int N, int H, int W, int C) {
+        Act a;
+        a.N = N, a.H = H, a.W = W, a.C = C;
+        void* p = nullptr;
+        if (cudaMalloc(&p, (size_t)a.plane() * 2 * h->planes) != cudaSuccess) {
+            rc = fail(h, -10, "cudaMalloc failed for activation tensor");
+            return a;
+        }
+        plan->allocs.push_back(p);
+        a.ptr = (__nv_bfloat16*)p;
+        return a;
+    }
+    ActF32 new_f32(int N, int H, int W, int C) {
+        ActF32 a;
+        a.N = N, a.H = H, a.W = W, a.C = C;
+        void* p = nullptr;
+        if (cudaMalloc(&p, (size_t)N * H * W * C * 4) != cudaSuccess) {
+            rc = fail(h, -10, "cudaMalloc failed for fp32 tensor");
+            return a;
+        }
+        plan->allocs.push_back(p);
+        a.ptr = (float*)p;
+        return a;
+    }
+    const ConvLayer* layer(const std::string& name) {
+        auto it = h->layers.find(name);
+        if (it == h->layers.end()) {
+            rc = fail(h, -41, "layer not found: " + name);
+            return nullptr;
+        }
+        return &it->second;
+    }
+    Act conv(const std::string& name, const Act& in, int relu, const Act* res = nullptr, const Act* p1 = nullptr,
+             const Act* p2 = nullptr) {
+        Act out;
+        if (rc) return out;
+        const ConvLayer* L = layer(name);
+        if (!L) return out;
+        const int Ho = (in.H + 2 * L->pad - L->k) / L->stride + 1, Wo = (in.W + 2 * L->pad - L->k) / L->stride + 1;
+        out = new_act(in.N, Ho, Wo, L->Cout_pad);
+        if (rc) return out;
+        Op op;
+        op.kind = OP_CONV;
+        rc = setup_conv(h, *L, in, res, p1, p2, &out, nullptr, relu, &op.cp, &op.block_n, &op.flops);
+        plan->ops.push_back(op);
+        plan->n_conv++;
+        plan->conv_flops += op.flops;
+        return out;
+    }
+    ActF32 conv_f32(const std::string& name, const Act& in) {
+        ActF32 out;
+        if (rc) return out;
+        const ConvLayer* L = layer(name);
+        if (!L) return out;
+        out = new_f32(in.N, in.H, in.W, L->Cout_pad);
+        if (rc) return out;
+        Op op;
+        op.kind = OP_CONV;
+        rc = setup_conv(h, *L, in, nullptr, nullptr, nullptr, nullptr, &out, 0, &op.cp, &op.block_n, &op.flops);
+        plan->ops.push_back(op);
+        plan->n_conv++;
+        plan->conv_flops += op.flops;
+        return out;
+    }
+};
+
+int build_plan(smapb_handle* h, int B, Plan** out_plan) {
+    auto it = h->plans.find(B);
+    if (it != h->plans.end()) {
+        *out_plan = it->second.get();
+        return 0;
+    }
+    std::unique_ptr<Plan> plan(new Plan());
+    plan->B = B;
+    PlanBuilder pb{h, plan.get(), B};
+    const int H = h->in_h, W = h->in_w;
+    static const int LAYERS[4] = {3, 4, 6, 3};
+    // stem + maxpool (model/smap.py:88-92)
+    Act stem = pb.new_act(B, H / 2, W / 2, 64);
+    {
+        Op op;
+        op.kind = OP_STEM;
+        op.out = stem;
+        plan->ops.push_back(op);
+    }
+    Act x = pb.new_act(B, H / 4, W / 4, 64);
+    {
+        Op op;
+        op.kind = OP_MAXPOOL;
+        op.a = stem;
+        op.out = x;
+        plan->ops.push_back(op);
+    }
+    Act skip1[4], skip2[4];
+    ActF32 res[4], resd3, resrd3;
+    for (int s = 0; s < 3 && !pb.rc; s++) {
+        const std::string pre = "stage" + std::to_string(s) + ".";
+        const bool gen_skip = s != 2;
+        Act feats[4];
+        Act t = x;
+        for (int li = 0; li < 4; li++) {
+            for (int b = 0; b < LAYERS[li]; b++) {
+                const std::string p = pre + "downsample.layer" + std::to_string(li + 1) + "." + std::to_string(b) + ".";
+                Act o1 = pb.conv(p + "conv_bn_relu1", t, 1);
+                Act o2 = pb.conv(p + "conv_bn_relu2", o1, 1);
+                Act idn = t;
+                if (b == 0) idn = pb.conv(p + "downsample", t, 0);
+                const bool last = (b == LAYERS[li] - 1) && s > 0;
+                // out = relu(conv3 + x) [ + skip1 + skip2 ]   (model/smap.py:74-75,143)
+                t = pb.conv(p + "conv_bn_relu3", o2, 1, &idn, last ? &skip1[li] : nullptr, last ? &skip2[li] : nullptr);
+            }
+            feats[li] = t;
+        }
+        Act up_x;
+        Act sk1[4], sk2[4];
+        Act cross;
+        for (int ind = 0; ind < 4 && !pb.rc; ind++) {
+            const std::string p = pre + "upsample.up" + std::to_string(ind + 1) + ".";
+            const Act& xin = feats[3 - ind];
+            Act out;
+            if (ind == 0) {
+                out = pb.conv(p + "u_skip", xin, 1);
+            } else {
+                Act a = pb.conv(p + "u_skip", xin, 0);
+                Act tl = pb.conv(p + "up_conv", up_x, 0);  // 1x1 conv commuted in front of the bilinear x2
+                out = pb.new_act(a.N, a.H, a.W, a.C);
+                Op op;
+                op.kind = OP_UPADD;
+                op.a = a;
+                op.b = tl;
+                op.out = out;
+                plan->ops.push_back(op);
+            }
+            // heads: only those that reach the returned tensors (model/smap.py:418-419) are computed
+            if (s == 2 && ind >= 1) {
+                Act r1 = pb.conv(p + "res_conv1", out, 1);
+                res[ind] = pb.conv_f32(p + "res_conv2", r1);
+            }
+            if (s == 2 && ind == 3) {
+                Act d1 = pb.conv(p + "res_d_conv1", out, 1);
+                resd3 = pb.conv_f32(p + "res_d_conv2", d1);
+                Act rd1 = pb.conv(p + "res_rd_conv1", out, 1);
+                resrd3 = pb.conv_f32(p + "res_rd_conv2", rd1);
+            }
+            if (gen_skip) {
+                sk1[ind] = pb.conv(p + "skip1", xin, 1);
+                sk2[ind] = pb.conv(p + "skip2", out, 1);
+                if (ind == 3) cross = pb.conv(p + "cross_conv", out, 1);
+            }
+            up_x = out;
+        }
+        for (int li = 0; li < 4; li++) {  // skip lists are finest-first (model/smap.py:281-282)
+            skip1[li] = sk1[3 - li];
+            skip2[li] = sk2[3 - li];
+        }
+        x = cross;
+    }
+    if (pb.rc) {
+        for (void* p : plan->allocs) cudaFree(p);
+        return pb.rc;
+    }
+    {
+        Op op;
+        op.kind = OP_HEADMERGE;
+        op.f4 = res[3], op.f3 = res[2], op.f2 = res[1];
+        op.cout = 43;
+        op.which_out = 0;
+        plan->ops.push_back(op);
+        Op od;
+        od.kind = OP_HEADMERGE;
+        od.f4 = resd3;
+        od.cout = 14;
+        od.which_out = 1;
+        plan->ops.push_back(od);
+        Op ord_;
+        ord_.kind = OP_HEADMERGE;
+        ord_.f4 = resrd3;
+        ord_.cout = 1;
+        ord_.which_out = 2;
+        plan->ops.push_back(ord_);
+    }
+    *out_plan = plan.get();
+    h->plans[B] = std::move(plan);
+    return 0;
+}
+
+int run_plan(smapb_handle* h, Plan* plan, const float* imgs, float* hm2d, float* detd, float* rootd,
+             cudaStream_t st) {
+    const int B = plan->B;
+    const int T = h->planes;
+    for (const Op& op : plan->ops) {
+        switch (op.kind) {
+            case OP_STEM:
+                CK(launch_stem(imgs, h->stem_w, h->stem_b, B, h->in_h, h->in_w, op.out.ptr, op.out.plane(), T, st));
+                break;
+            case OP_MAXPOOL:
+                CK(launch_maxpool(op.a.ptr, op.a.plane(), B, op.a.H, op.a.W, op.a.C, op.out.ptr, op.out.plane(), T, st));
+                break;
+            case OP_CONV:
+                CK(launch_conv(op.cp, op.block_n, h->nterms, h->sm_count, st, false));
+                break;
+            case OP_UPADD:
+                CK(launch_upadd_relu(op.a.ptr, op.a.plane(), op.b.ptr, op.b.plane(), B, op.a.H, op.a.W, op.b.H, op.b.W,
+                                     op.a.C, op.out.ptr, op.out.plane(), T, st));
+                break;
+            case OP_HEADMERGE: {
+                float* dst = op.which_out == 0 ? hm2d : op.which_out == 1 ? detd : rootd;
+                CK(launch_head_merge(op.f4.ptr, op.f3.ptr, op.f2.ptr, B, op.f4.H, op.f4.W, op.f3.H, op.f3.W, op.f2.H,
+                                     op.f2.W, op.f4.C, op.cout, dst, st));
+                break;
+            }
+        }
+        h->launches++;
+    }
+    return 0;
+}
+
+}  // namespace
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+extern "C" {
+#pragma GCC visibility push(default)
+
+int smapb_version(void) { return 100; }
+
+const char* smapb_last_error(const smapb_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int smapb_create(smapb_handle** out, int device, int max_batch, int in_h, int in_w) {
+    if (!out) return -1;
+    *out = nullptr;
+    if (max_batch < 1 || in_h % 32 || in_w % 32 || in_h < 32 || in_w < 32) {
+        g_create_error = "smapb_create: max_batch >= 1 and in_h, in_w multiples of 32 required";
+        return -1;
+    }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || device >= ndev) {
+        g_create_error = std::string("smapb_create: no usable CUDA device (") + cudaGetErrorString(e) + ")";
+        return -2;
+    }
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, device);
+    if (prop.major != 10) {
+        g_create_error = "smapb_create: this library contains sm_100a code only (device is sm_" +
+                         std::to_string(prop.major) + std::to_string(prop.minor) + ")";
+        return -3;
+    }
+    cudaSetDevice(device);
+    smapb_handle* h = new smapb_handle();
+    h->device = device;
+    h->max_batch = max_batch;
+    h->in_h = in_h, h->in_w = in_w;
+    h->h = in_h / 4, h->w = in_w / 4;
+    h->sm_count = prop.multiProcessorCount;
+    const size_t hw = (size_t)h->h * h->w;
+    const size_t MB = max_batch;
+    int rc = 0;
+    rc |= dev_alloc(h, &h->peaks, MB * NJ * (MAXP + 1) * 3);
+    rc |= dev_alloc(h, &h->scores, MB * NL * MAXP * MAXP);
+    rc |= dev_alloc(h, &h->bodies, MB * MAXP * NJ * 4);
+    rc |= dev_alloc(h, &h->counts, MB);
+    rc |= dev_alloc(h, &h->imgs_dev, MB * 3 * in_h * in_w);
+    rc |= dev_alloc(h, &h->hm, MB * NC2D * hw);
+    rc |= dev_alloc(h, &h->detd, MB * NL * hw);
+    rc |= dev_alloc(h, &h->rootd, MB * hw);
+    rc |= dev_alloc(h, &h->scales_dev, MB * SMAPB_SCALE_LEN);
+    rc |= dev_alloc(h, &h->records_dev, MB);
+    if (rc) {
+        g_create_error = h->err;
+        delete h;
+        return -10;
+    }
+    const char* aerr = nullptr;
+    // association kernels stage whole planes in shared memory; larger maps are rejected at call time
+    if (assoc_configure(h->h, h->w, &aerr) != 0) h->err = aerr ? aerr : "assoc_configure failed";
+    *out = h;
+    return 0;
+}
+
+void smapb_destroy(smapb_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    for (auto& kv : h->plans) {
+        if (kv.second->graph) cudaGraphExecDestroy(kv.second->graph);
+        for (void* p : kv.second->allocs) cudaFree(p);
+    }
+    for (auto& kv : h->layers) {
+        cudaFree(kv.second.w_dev);
+        cudaFree(kv.second.bias_dev);
+    }
+    void* ptrs[] = {h->peaks, h->scores, h->bodies, h->counts, h->imgs_dev, h->imgs_flip, h->hm, h->hm_flip, h->detd,
+                    h->rootd, h->scratch_detd, h->scratch_rootd, h->scales_dev, h->records_dev, h->stem_w, h->stem_b};
+    for (void* p : ptrs)
+        if (p) cudaFree(p);
+    delete h;
+}
+
+int smapb_load_weight(smapb_handle* h, const char* key, const float* host, const int64_t* shape, int ndim) {
+    if (!h || !key || !host) return -1;
+    const std::string k(key);
+    if (k.size() > 19 && k.compare(k.size() - 19, 19, "num_batches_tracked") == 0) return 0;
+    size_t n = 1;
+    std::vector<int64_t> shp;
+    for (int i = 0; i < ndim; i++) {
+        n *= (size_t)shape[i];
+        shp.push_back(shape[i]);
+    }
+    h->raw[k].assign(host, host + n);
+    h->raw_shape[k] = shp;
+    h->finalized = false;
+    return 0;
+}
+
+int smapb_finalize_weights(smapb_handle* h, int precision) {
+    if (!h) return -1;
+    if (precision != SMAPB_PREC_BF16X3 && precision != SMAPB_PREC_BF16) return fail(h, -1, "unknown precision");
+    cudaSetDevice(h->device);
+    // a new weight set invalidates cached plans (they hold tensor maps over the old weight buffers only if
+    // buffers are re-allocated; buffers are reused in place, but the plane count may change)
+    const int new_planes = precision == SMAPB_PREC_BF16X3 ? 2 : 1;
+    if (new_planes != h->planes || !h->plans.empty()) {
+        for (auto& kv : h->plans) {
+            if (kv.second->graph) cudaGraphExecDestroy(kv.second->graph);
+            for (void* p : kv.second->allocs) cudaFree(p);
+        }
+        h->plans.clear();
+        for (auto& kv : h->layers) {
+            cudaFree(kv.second.w_dev);
+            cudaFree(kv.second.bias_dev);
+        }
+        h->layers.clear();
+    }
+    h->nterms = precision;
+    h->planes = new_planes;
+    // unit names: every "<name>.conv.weight" key
+    std::vector<std::string> units;
+    for (auto& kv : h->raw) {
+        const std::string& k = kv.first;
+        const std::string suf = ".conv.weight";
+        if (k.size() > suf.size() && k.compare(k.size() - suf.size(), suf.size(), suf) == 0)
+            units.push_back(k.substr(0, k.size() - suf.size()));
+    }
+    if (units.empty()) return fail(h, -40, "no weights loaded");
+    for (const std::string& name : units) {
+        std::vector<float> wf, bf;
+        int Cout, Cin, k;
+        int rc = fold_unit(h, name, &wf, &bf, &Cout, &Cin, &k);
+        if (rc) return rc;
+        if (name == "top.conv") {
+            if (Cin != 3 || Cout != 64 || k != 7) return fail(h, -40, "top.conv must be 3->64 7x7");
+            std::vector<float> w2(147 * 64);
+            for (int co = 0; co < 64; co++)
+                for (int ci = 0; ci < 3; ci++)
+                    for (int ky = 0; ky < 7; ky++)
+                        for (int kx = 0; kx < 7; kx++)
+                            w2[((ky * 7 + kx) * 3 + ci) * 64 + co] = wf[((co * 3 + ci) * 7 + ky) * 7 + kx];
+            if (!h->stem_w) {
+                if (dev_alloc(h, &h->stem_w, w2.size())) return -10;
+                if (dev_alloc(h, &h->stem_b, 64)) return -10;
+            }
+            CK(cudaMemcpy(h->stem_w, w2.data(), w2.size() * 4, cudaMemcpyHostToDevice));
+            CK(cudaMemcpy(h->stem_b, bf.data(), 64 * 4, cudaMemcpyHostToDevice));
+            continue;
+        }
+        ConvLayer& L = h->layers[name];
+        L.name = name;
+        L.Cin = Cin;
+        L.Cout = Cout;
+        L.Cout_pad = pad32(Cout);
+        L.k = k;
+        L.pad = k / 2;
+        // stride: first 3x3 / downsample of layer2..4 (model/smap.py:103-108,124-136)
+        L.stride = 1;
+        {
+            const size_t pl = name.find(".downsample.layer");
+            if (pl != std::string::npos) {
+                const int li = name[pl + 17] - '0';
+                const size_t pb = name.find('.', pl + 18);
+                const int blk = atoi(name.c_str() + pl + 19);
+                (void)pb;
+                const bool first = blk == 0;
+                const bool is_c2 = name.find("conv_bn_relu2") != std::string::npos;
+                const bool is_ds = name.size() > 11 && name.compare(name.size() - 11, 11, ".downsample") == 0;
+                if (li >= 2 && first && (is_c2 || is_ds)) L.stride = 2;
+            }
+        }
+        int rc2 = upload_conv_layer(h, L, wf, bf);
+        if (rc2) return rc2;
+    }
+    if (!h->stem_w) return fail(h, -40, "top.conv weights missing");
+    h->finalized = true;
+    return 0;
+}
+
+int smapb_backbone_forward(smapb_handle* h, const float* imgs, int B, float* hm2d, float* detd, float* rootd,
+                           void* stream) {
+    if (!h) return -1;
+    if (!h->finalized) return fail(h, -2, "smapb_backbone_forward: weights not finalized");
+    if (B < 1) return fail(h, -1, "B < 1");
+    cudaSetDevice(h->device);
+    Plan* plan = nullptr;
+    int rc = build_plan(h, B, &plan);
+    if (rc) return rc;
+    return run_plan(h, plan, imgs, hm2d, detd, rootd, (cudaStream_t)stream);
+}
+
+int smapb_merge_scale(smapb_handle* h, float* hm2d, const float* hm2d_flip, int B, int do_scale, void* stream) {
+    if (!h) return -1;
+    cudaSetDevice(h->device);
+    CK(launch_merge_scale(hm2d, hm2d_flip, B, h->h, h->w, do_scale, (cudaStream_t)stream));
+    h->launches++;
+    return 0;
+}
+
+static int check_assoc(smapb_handle* h, int B) {
+    if (B < 1 || B > h->max_batch) return fail(h, -1, "association: B outside [1, max_batch]");
+    const char* aerr = nullptr;
+    if (assoc_configure(h->h, h->w, &aerr) != 0) return fail(h, -3, aerr ? aerr : "assoc_configure failed");
+    return 0;
+}
+
+int smapb_assoc_extract(smapb_handle* h, const float* hms, int B, float* peaks, float* pair_scores, void* stream) {
+    if (!h) return -1;
+    cudaSetDevice(h->device);
+    int rc = check_assoc(h, B);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(launch_nms(hms, NC2D, B, h->h, h->w, 0.2f, peaks, st));
+    CK(launch_paf(hms, NC2D, B, h->h, h->w, peaks, pair_scores, 1, st));
+    h->launches += 2;
+    return 0;
+}
+
+int smapb_assoc_connect(smapb_handle* h, const float* hms, const float* rdepth, int B, int root_idx, int dist_flag,
+                        float* bodies, int* counts, void* stream) {
+    if (!h) return -1;
+    cudaSetDevice(h->device);
+    int rc = check_assoc(h, B);
+    if (rc) return rc;
+    if (root_idx < 0 || root_idx >= NJ) return fail(h, -1, "root_idx out of range");
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(launch_nms(hms, NC2D, B, h->h, h->w, 0.2f, h->peaks, st));
+    CK(launch_paf(hms, NC2D, B, h->h, h->w, h->peaks, h->scores, 0, st));
+    CK(launch_group(h->peaks, h->scores, rdepth, B, h->h, h->w, root_idx, dist_flag, bodies, counts, st));
+    h->launches += 3;
+    return 0;
+}
+
+int smapb_lift3d(smapb_handle* h, const float* bodies, const int* counts, const float* detd, const float* rootd,
+                 const double* scales, int B, float* pred2d, double* pred3d, double* root_depth, int* counts_out,
+                 void* stream) {
+    if (!h) return -1;
+    cudaSetDevice(h->device);
+    if (B < 1) return fail(h, -1, "B < 1");
+    CK(launch_lift(bodies, counts, detd, rootd, scales, B, h->h, h->w, 2, pred2d, pred3d, root_depth, counts_out,
+                   (long long)MAXP * NJ * 4, (long long)MAXP * NJ * 4, MAXP, 1, (cudaStream_t)stream));
+    h->launches++;
+    return 0;
+}
+
+// flip along W of an NCHW fp32 batch (torch.flip(imgs, [-1]), exps/stage3_root2/test.py:56)
+__global__ void flip_w_kernel(const float* __restrict__ in, float* __restrict__ out, long long rows, int W) {
+    const long long total = rows * W;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / W;
+        const int x = (int)(i - r * W);
+        out[i] = in[r * W + (W - 1 - x)];
+    }
+}
+
+int smapb_infer_device(smapb_handle* h, const float* imgs, const double* scales, int B, int do_flip,
+                       smapb_record* records, void* stream) {
+    if (!h) return -1;
+    if (!h->finalized) return fail(h, -2, "smapb_infer_device: weights not finalized");
+    cudaSetDevice(h->device);
+    int rc = check_assoc(h, B);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    Plan* plan = nullptr;
+    rc = build_plan(h, B, &plan);
+    if (rc) return rc;
+    rc = run_plan(h, plan, imgs, h->hm, h->detd, h->rootd, st);
+    if (rc) return rc;
+    const size_t hw = (size_t)h->h * h->w;
+    if (do_flip) {
+        const size_t MB = h->max_batch;
+        if (!h->imgs_flip) {
+            if (dev_alloc(h, &h->imgs_flip, MB * 3 * h->in_h * h->in_w)) return -10;
+            if (dev_alloc(h, &h->hm_flip, MB * NC2D * hw)) return -10;
+            if (dev_alloc(h, &h->scratch_detd, MB * NL * hw)) return -10;
+            if (dev_alloc(h, &h->scratch_rootd, MB * hw)) return -10;
+        }
+        flip_w_kernel<<<148 * 8, 256, 0, st>>>(imgs, h->imgs_flip, (long long)B * 3 * h->in_h, h->in_w);
+        CK(cudaGetLastError());
+        h->launches++;
+        rc = run_plan(h, plan, h->imgs_flip, h->hm_flip, h->scratch_detd, h->scratch_rootd, st);
+        if (rc) return rc;
+    }
+    CK(launch_merge_scale(h->hm, do_flip ? h->hm_flip : nullptr, B, h->h, h->w, 1, st));
+    CK(launch_nms(h->hm, NC2D, B, h->h, h->w, 0.2f, h->peaks, st));
+    CK(launch_paf(h->hm, NC2D, B, h->h, h->w, h->peaks, h->scores, 0, st));
+    CK(launch_group(h->peaks, h->scores, h->rootd, B, h->h, h->w, 2, 1, h->bodies, h->counts, st));
+    char* rb = reinterpret_cast<char*>(records);
+    CK(launch_lift(h->bodies, h->counts, h->detd, h->rootd, scales, B, h->h, h->w, 2,
+                   reinterpret_cast<float*>(rb + offsetof(smapb_record, pred2d)),
+                   reinterpret_cast<double*>(rb + offsetof(smapb_record, pred3d)),
+                   reinterpret_cast<double*>(rb + offsetof(smapb_record, root_depth)),
+                   reinterpret_cast<int*>(rb + offsetof(smapb_record, count)), sizeof(smapb_record) / 4,
+                   sizeof(smapb_record) / 8, sizeof(smapb_record) / 8, sizeof(smapb_record) / 4, st));
+    h->launches += 5;
+    return 0;
+}
+
+int smapb_infer_host(smapb_handle* h, const float* imgs_host, const double* scales_host, int B, int do_flip,
+                     smapb_record* records_host, void* stream) {
+    if (!h) return -1;
+    if (B < 1 || B > h->max_batch) return fail(h, -1, "smapb_infer_host: B outside [1, max_batch]");
+    cudaSetDevice(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaMemcpyAsync(h->imgs_dev, imgs_host, (size_t)B * 3 * h->in_h * h->in_w * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->scales_dev, scales_host, (size_t)B * SMAPB_SCALE_LEN * 8, cudaMemcpyHostToDevice, st));
+    int rc = smapb_infer_device(h, h->imgs_dev, h->scales_dev, B, do_flip, h->records_dev, stream);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(records_host, h->records_dev, (size_t)B * sizeof(smapb_record), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int64_t smapb_launch_count(const smapb_handle* h) { return h ? h->launches : 0; }
+
+int smapb_plan_info(const smapb_handle* hc, int B, int* n_conv, double* conv_flops) {
+    smapb_handle* h = const_cast<smapb_handle*>(hc);
+    if (!h) return -1;
+    if (!h->finalized) return fail(h, -2, "weights not finalized");
+    cudaSetDevice(h->device);
+    Plan* plan = nullptr;
+    int rc = build_plan(h, B, &plan);
+    if (rc) return rc;
+    if (n_conv) *n_conv = plan->n_conv;
+    if (conv_flops) *conv_flops = plan->conv_flops;
+    return 0;
+}
+
+// split-bf16 planes -> fp32 (test hook)
+__global__ void split_to_f32_kernel(const __nv_bfloat16* __restrict__ in, long long plane, int terms, float* __restrict__ out,
+                                    long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float v = __bfloat162float(in[i]);
+    if (terms == 2) v += __bfloat162float(in[plane + i]);
+    out[i] = v;
+}
+
+int smapb_conv_test(smapb_handle* h, const float* x, const float* w, const float* bias, const float* res, int B,
+                    int H, int W, int Cin, int Cout, int k, int stride, int relu, int precision, float* y,
+                    float* ms_out, void* stream) {
+    if (!h) return -1;
+    cudaSetDevice(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int save_terms = h->nterms, save_planes = h->planes;
+    h->nterms = precision == SMAPB_PREC_BF16 ? 1 : 3;
+    h->planes = precision == SMAPB_PREC_BF16 ? 1 : 2;
+    int rc = 0;
+    ConvLayer L;
+    L.name = "conv_test";
+    L.Cin = Cin, L.Cout = Cout, L.Cout_pad = pad32(Cout), L.k = k, L.stride = stride, L.pad = k / 2, L.relu = relu;
+    std::vector<float> wh((size_t)Cout * Cin * k * k), bh(Cout);
+    std::vector<void*> tmp;
+    auto cleanup = [&]() {
+        for (void* p : tmp) cudaFree(p);
+        cudaFree(L.w_dev);
+        cudaFree(L.bias_dev);
+        h->nterms = save_terms;
+        h->planes = save_planes;
+    };
+#define CKT(call)                                                                         \
+    do {                                                                                  \
+        cudaError_t e_ = (call);                                                          \
+        if (e_ != cudaSuccess) {                                                          \
+            cleanup();                                                                    \
+            return fail(h, -10, std::string(#call) + ": " + cudaGetErrorString(e_));      \
+        }                                                                                 \
+    } while (0)
+    CKT(cudaMemcpy(wh.data(), w, wh.size() * 4, cudaMemcpyDeviceToHost));
+    CKT(cudaMemcpy(bh.data(), bias, bh.size() * 4, cudaMemcpyDeviceToHost));
+    rc = upload_conv_layer(h, L, wh, bh);
+    if (rc) {
+        cleanup();
+        return rc;
+    }
+    const int Ho = (H + 2 * L.pad - k) / stride + 1, Wo = (W + 2 * L.pad - k) / stride + 1;
+    Act in, out, r;
+    in.N = B, in.H = H, in.W = W, in.C = Cin;
+    out.N = B, out.H = Ho, out.W = Wo, out.C = L.Cout_pad;
+    r = out;
+    void* p = nullptr;
+    CKT(cudaMalloc(&p, (size_t)in.plane() * 2 * h->planes));
+    tmp.push_back(p);
+    in.ptr = (__nv_bfloat16*)p;
+    CKT(cudaMalloc(&p, (size_t)out.plane() * 2 * h->planes));
+    tmp.push_back(p);
+    out.ptr = (__nv_bfloat16*)p;
+    CKT(launch_f32_to_split(x, in.ptr, in.plane(), in.plane(), h->planes, st));
+    if (res) {
+        if (L.Cout_pad != Cout) {
+            cleanup();
+            return fail(h, -1, "conv_test: residual requires Cout % 32 == 0");
+        }
+        CKT(cudaMalloc(&p, (size_t)out.plane() * 2 * h->planes));
+        tmp.push_back(p);
+        r.ptr = (__nv_bfloat16*)p;
+        CKT(launch_f32_to_split(res, r.ptr, r.plane(), r.plane(), h->planes, st));
+    }
+    ConvParams cp;
+    int bn = 0;
+    rc = setup_conv(h, L, in, res ? &r : nullptr, nullptr, nullptr, &out, nullptr, relu, &cp, &bn, nullptr);
+    if (rc) {
+        cleanup();
+        return rc;
+    }
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    CKT(launch_conv(cp, bn, h->nterms, h->sm_count, st, false));  // warm-up + result
+    const int reps = ms_out ? 5 : 0;
+    cudaEventRecord(e0, st);
+    for (int i = 0; i < reps; i++) CKT(launch_conv(cp, bn, h->nterms, h->sm_count, st, false));
+    cudaEventRecord(e1, st);
+    h->launches += 1 + reps;
+    // de-pad + convert
+    float* ytmp = nullptr;
+    CKT(cudaMalloc((void**)&ytmp, (size_t)out.plane() * 4));
+    tmp.push_back(ytmp);
+    split_to_f32_kernel<<<(unsigned)((out.plane() + 255) / 256), 256, 0, st>>>(out.ptr, out.plane(), h->planes, ytmp,
+                                                                               out.plane());
+    CKT(cudaGetLastError());
+    CKT(cudaMemcpy2DAsync(y, (size_t)Cout * 4, ytmp, (size_t)L.Cout_pad * 4, (size_t)Cout * 4, (size_t)B * Ho * Wo,
+                          cudaMemcpyDeviceToDevice, st));
+    CKT(cudaStreamSynchronize(st));
+    if (ms_out) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        *ms_out = ms / reps;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cleanup();
+    return 0;
+#undef CKT
+}
+
+#pragma GCC visibility pop
+}  // extern "C"

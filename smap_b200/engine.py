@@ -1,0 +1,180 @@
+"""Python host side of the hot path: a thin, torch-tensor-facing wrapper over the C ABI.
+
+torch is plumbing only (device memory, streams); every kernel runs inside libsmap_b200.so."""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import MAXP, NC2D, NJ, NL, PREC_BF16, PREC_BF16X3, RECORD_BYTES, SCALE_LEN, SmapB200Error
+
+RECORD_DTYPE = np.dtype([("pred3d", "<f8", (MAXP, NJ, 4)), ("root_depth", "<f8", (MAXP,)),
+                         ("pred2d", "<f4", (MAXP, NJ, 4)), ("count", "<i4"), ("pad_", "<i4")])
+assert RECORD_DTYPE.itemsize == RECORD_BYTES
+
+PRECISIONS = {"bf16x3": PREC_BF16X3, "bf16": PREC_BF16}
+
+
+def scale_row(scale):
+    """dict (exps/stage3_root2/test.py:99-103 layout) -> float64[9]."""
+    return np.array([scale["scale"], scale["img_width"], scale["img_height"], scale["net_width"],
+                     scale["net_height"], scale["f_x"], scale["f_y"], scale["cx"], scale["cy"]], np.float64)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class Engine:
+    """One handle per (process, device).  in_h/in_w: network input size (multiples of 32)."""
+
+    def __init__(self, device=0, max_batch=8, in_h=512, in_w=832):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise SmapB200Error("smap_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        self.device = torch.device("cuda", device)
+        self.max_batch, self.in_h, self.in_w = max_batch, in_h, in_w
+        self.h, self.w = in_h // 4, in_w // 4
+        hp = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            rc = self.lib.smapb_create(ctypes.byref(hp), device, max_batch, in_h, in_w)
+        if rc != 0:
+            raise SmapB200Error("smapb_create failed (%d): %s" % (rc, self.lib.smapb_last_error(None).decode()))
+        self._h = hp
+        self.precision = None
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.smapb_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise SmapB200Error("%s failed (%d): %s" % (what, rc, self.lib.smapb_last_error(self._h).decode()))
+
+    # ---- weights ------------------------------------------------------------------------------
+    def load_state_dict(self, sd, precision="bf16x3"):
+        """sd: reference schema (model/smap.py, 1876 keys); tensors or arrays, any device."""
+        for k, v in sd.items():
+            if k.endswith("num_batches_tracked"):
+                continue
+            a = v.detach().cpu().float().contiguous().numpy() if torch.is_tensor(v) else np.ascontiguousarray(v, np.float32)
+            shape = (ctypes.c_int64 * max(1, a.ndim))(*a.shape)
+            self._check(self.lib.smapb_load_weight(self._h, k.encode(), a.ctypes.data_as(ctypes.c_void_p), shape, a.ndim),
+                        "smapb_load_weight(%s)" % k)
+        self._check(self.lib.smapb_finalize_weights(self._h, PRECISIONS[precision]), "smapb_finalize_weights")
+        self.precision = precision
+
+    # ---- backbone -----------------------------------------------------------------------------
+    def forward(self, imgs):
+        """imgs fp32 NCHW cuda [B,3,in_h,in_w] -> (hm2d [B,43,h,w], det_d [B,14,h,w], root_d [B,1,h,w])."""
+        assert imgs.is_cuda and imgs.dtype == torch.float32 and imgs.shape[1:] == (3, self.in_h, self.in_w)
+        imgs = imgs.contiguous()
+        B = imgs.shape[0]
+        hm = torch.empty(B, NC2D, self.h, self.w, device=imgs.device)
+        dd = torch.empty(B, NL, self.h, self.w, device=imgs.device)
+        rd = torch.empty(B, 1, self.h, self.w, device=imgs.device)
+        self._check(self.lib.smapb_backbone_forward(self._h, _ptr(imgs), B, _ptr(hm), _ptr(dd), _ptr(rd), _stream()),
+                    "smapb_backbone_forward")
+        return hm, dd, rd
+
+    def merge_scale(self, hm, hm_flip=None, do_scale=True):
+        self._check(self.lib.smapb_merge_scale(self._h, _ptr(hm), _ptr(hm_flip), hm.shape[0], int(do_scale), _stream()),
+                    "smapb_merge_scale")
+        return hm
+
+    # ---- association --------------------------------------------------------------------------
+    def extract(self, hms):
+        """hms fp32 cuda [B,43,h,w] (already /255,/127) -> peaks [B,15,128,3], pair scores [B,14,127,127]."""
+        hms = hms.contiguous()
+        B = hms.shape[0]
+        peaks = torch.empty(B, NJ, MAXP + 1, 3, device=hms.device)
+        scores = torch.empty(B, NL, MAXP, MAXP, device=hms.device)
+        self._check(self.lib.smapb_assoc_extract(self._h, _ptr(hms), B, _ptr(peaks), _ptr(scores), _stream()),
+                    "smapb_assoc_extract")
+        return peaks, scores
+
+    def connect(self, hms, rdepth, root_idx=2, dist_flag=True):
+        """-> bodies [B,127,15,4] (x,y,0,score; heat-map px), counts int32 [B]; device tensors."""
+        hms = hms.contiguous()
+        rdepth = rdepth.contiguous()
+        B = hms.shape[0]
+        bodies = torch.empty(B, MAXP, NJ, 4, device=hms.device)
+        counts = torch.empty(B, dtype=torch.int32, device=hms.device)
+        self._check(self.lib.smapb_assoc_connect(self._h, _ptr(hms), _ptr(rdepth), B, root_idx, int(dist_flag),
+                                                 _ptr(bodies), _ptr(counts), _stream()), "smapb_assoc_connect")
+        return bodies, counts
+
+    def lift(self, bodies, counts, det_d, root_d, scales):
+        """scales: float64 cuda [B,9].  -> pred2d [B,127,15,4] f32, pred3d f64, root_depth [B,127] f64, counts."""
+        B = bodies.shape[0]
+        dev = bodies.device
+        p2 = torch.empty(B, MAXP, NJ, 4, device=dev)
+        p3 = torch.empty(B, MAXP, NJ, 4, device=dev, dtype=torch.float64)
+        rdp = torch.empty(B, MAXP, device=dev, dtype=torch.float64)
+        co = torch.empty(B, dtype=torch.int32, device=dev)
+        self._check(self.lib.smapb_lift3d(self._h, _ptr(bodies.contiguous()), _ptr(counts), _ptr(det_d.contiguous()),
+                                          _ptr(root_d.contiguous()), _ptr(scales.contiguous()), B, _ptr(p2), _ptr(p3),
+                                          _ptr(rdp), _ptr(co), _stream()), "smapb_lift3d")
+        return p2, p3, rdp, co
+
+    # ---- whole path ---------------------------------------------------------------------------
+    def infer_device(self, imgs, scales, do_flip=False):
+        """imgs cuda fp32 [B,3,H,W], scales cuda f64 [B,9] -> records uint8 cuda [B, RECORD_BYTES]."""
+        B = imgs.shape[0]
+        rec = torch.empty(B, RECORD_BYTES, dtype=torch.uint8, device=imgs.device)
+        self._check(self.lib.smapb_infer_device(self._h, _ptr(imgs.contiguous()), _ptr(scales.contiguous()), B,
+                                                int(do_flip), _ptr(rec), _stream()), "smapb_infer_device")
+        return rec
+
+    def infer_host(self, imgs, scales, do_flip=False, out=None):
+        """Host buffers in, host records out (synchronous).  imgs: CPU fp32 tensor (pinned preferred) [B,3,H,W];
+        scales: CPU float64 [B,9].  Returns a numpy structured array of RECORD_DTYPE [B]."""
+        assert not imgs.is_cuda and imgs.dtype == torch.float32
+        B = imgs.shape[0]
+        if out is None:
+            out = torch.empty(B, RECORD_BYTES, dtype=torch.uint8).pin_memory()
+        scales = torch.as_tensor(scales, dtype=torch.float64).contiguous()
+        self._check(self.lib.smapb_infer_host(self._h, _ptr(imgs.contiguous()), _ptr(scales), B, int(do_flip),
+                                              _ptr(out), _stream()), "smapb_infer_host")
+        return out.numpy().view(RECORD_DTYPE).reshape(B)
+
+    # ---- introspection ------------------------------------------------------------------------
+    def launch_count(self):
+        return int(self.lib.smapb_launch_count(self._h))
+
+    def plan_info(self, B):
+        n = ctypes.c_int()
+        f = ctypes.c_double()
+        self._check(self.lib.smapb_plan_info(self._h, B, ctypes.byref(n), ctypes.byref(f)), "smapb_plan_info")
+        return n.value, f.value
+
+    def conv_test(self, x, w, bias, res=None, stride=1, relu=True, precision="bf16x3", time_it=False):
+        """x fp32 NHWC cuda; w [Cout,Cin,k,k]; returns y fp32 NHWC (and ms)."""
+        B, H, W, Cin = x.shape
+        Cout, _, k, _ = w.shape
+        pad = k // 2
+        Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+        y = torch.empty(B, Ho, Wo, Cout, device=x.device)
+        ms = ctypes.c_float(0)
+        self._check(self.lib.smapb_conv_test(self._h, _ptr(x.contiguous()), _ptr(w.contiguous()), _ptr(bias.contiguous()),
+                                             _ptr(res.contiguous() if res is not None else None), B, H, W, Cin, Cout, k,
+                                             stride, int(relu), PRECISIONS[precision], _ptr(y),
+                                             ctypes.byref(ms) if time_it else None, _stream()), "smapb_conv_test")
+        return (y, ms.value) if time_it else y
+
+
+def records_to_numpy(rec):
+    """uint8 cuda/cpu tensor [B, RECORD_BYTES] -> numpy structured array [B]."""
+    return rec.cpu().numpy().view(RECORD_DTYPE).reshape(rec.shape[0])

@@ -15,8 +15,8 @@ import numpy as np
 LIMBS = [[0, 1], [0, 2], [0, 9], [9, 10], [10, 11], [0, 3], [3, 4], [4, 5],
          [2, 12], [12, 13], [13, 14], [2, 6], [6, 7], [7, 8]]
 
-# canonical MPI-15 template in (heat-map px x depth) units, y down, pelvis at origin;
-# bone lengths follow extensions/association.cpp:27-31.
+# canonical MPI-15 template in (net-input px x depth) units, y down, pelvis at origin; bone lengths follow
+# extensions/association.cpp:27-31 (the table is in input pixels: the grouping divides by dsScale = 4).
 _T = np.zeros((15, 2), np.float64)
 _T[2] = (0, 0)            # pelvis
 _T[0] = (0, -48.37)       # neck
@@ -46,14 +46,14 @@ def make_scene(seed, persons=15, h=128, w=208, noise=0.01, sigma=1.5):
     pafz = np.zeros((14, h, w), np.float64)
     cnt = np.zeros((14, h, w), np.float64)
     root_d = np.zeros((h, w), np.float64)
-    depth = np.sort(rng.uniform(2.0, 8.0, persons)) + np.arange(persons) * 1e-3
+    depth = np.sort(rng.uniform(0.5, 2.0, persons)) + np.arange(persons) * 1e-3
     rng.shuffle(depth)
     joints = np.zeros((persons, 15, 2))
     for p in range(persons):
         d = depth[p]
         ang = rng.normal(0, 0.15)
         rot = np.array([[np.cos(ang), -np.sin(ang)], [np.sin(ang), np.cos(ang)]])
-        tpl = (_T + rng.normal(0, 1.5, _T.shape)) @ rot.T / d
+        tpl = (_T + rng.normal(0, 1.5, _T.shape)) @ rot.T / (4.0 * d)
         ext = np.abs(tpl).max(0)
         cx = rng.uniform(4 + ext[0], w - 5 - ext[0]) if w - 5 - ext[0] > 4 + ext[0] else w / 2
         lo, hi = 4 + (-tpl[:, 1].min()), h - 5 - tpl[:, 1].max()
@@ -74,7 +74,9 @@ def make_scene(seed, persons=15, h=128, w=208, noise=0.01, sigma=1.5):
             rx, ry = xx - j[a, 0], yy - j[a, 1]
             along = rx * u[0] + ry * u[1]
             perp = np.abs(rx * u[1] - ry * u[0])
-            m = (along >= -1) & (along <= n + 1) & (perp <= 1.0)
+            # support is 2 px wide: the reference samples the PAF at (int)(x + 0.5) of the +0.5-offset peak
+            # coordinates, i.e. up to one pixel off the segment (bodyPartConnectorBase.cu:38-39)
+            m = (along >= -2) & (along <= n + 2) & (perp <= 2.0)
             paf[l, 0][m] += u[0]
             paf[l, 1][m] += u[1]
             pafz[l][m] += zj[b] - zj[a]

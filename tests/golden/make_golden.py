@@ -1,0 +1,127 @@
+"""Generates the committed golden fixtures by importing the REFERENCE (read-only, /root/reference) in the
+build container.  The fixtures travel to the GPU box; /root/reference does not.
+
+  backbone_64x96.npz : outputs of the unmodified reference model.smap.SMAP (CPU fp32) on a seeded input with
+                       seeded weights (oracle.smap_torch.make_state_dict / make_input are pure generators, the
+                       numbers come from the reference module's forward), for both BN settings, plus the
+                       flip-TTA merge computed with the reference's own loop (exps/stage3_root2/test.py:55-70).
+  lift_cases.npz     : inputs/outputs of the unmodified reference register_pred / generate_relZ / gen_3d_pose
+                       (exps/stage3_root2/test_util.py, lib/utils/post_3d.py) driven exactly as
+                       exps/stage3_root2/test.py:116-134 does, including cv2 INTER_NEAREST up-sampling.
+
+Run:  python tests/golden/make_golden.py
+"""
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = "/root/reference"
+sys.path.insert(0, ROOT)
+sys.path.insert(0, HERE)
+sys.path.insert(0, REF)
+sys.path.insert(0, os.path.join(REF, "exps", "stage3_root2"))
+
+from oracle.smap_torch import make_input, make_state_dict  # noqa: E402
+
+
+class NS(types.SimpleNamespace):
+    pass
+
+
+def golden_backbone():
+    from model.smap import SMAP
+
+    H, W = 64, 96
+    cfg = NS(MODEL=NS(STAGE_NUM=3, UPSAMPLE_CHANNEL_NUM=256), DATASET=NS(KEYPOINT=NS(NUM=15), PAF=NS(NUM=14)),
+             OUTPUT_SHAPE=(H // 4, W // 4), LOSS=NS(OHKM=True, TOPK=8, COARSE_TO_FINE=True))
+    out = {}
+    for bn, seed in (("identity", 11), ("random", 12)):
+        m = SMAP(cfg).eval()
+        m.load_state_dict(make_state_dict(seed, bn))
+        x = make_input(2, H, W, seed=seed + 100)
+        with torch.no_grad():
+            o2d, dd, rd = m(x)
+            f2d, _, _ = m(torch.flip(x, [-1]))
+        out["%s_hm2d" % bn] = o2d.numpy().copy()
+        out["%s_detd" % bn] = dd.numpy().copy()
+        out["%s_rootd" % bn] = rd.numpy().copy()
+        # flip merge exactly as test.py:55-70
+        kpt_num = 15
+        o = o2d.clone()
+        f = torch.flip(f2d, dims=[-1])
+        keypoint_pair = [0, 1, 2, 9, 10, 11, 12, 13, 14, 3, 4, 5, 6, 7, 8]
+        paf_pair = [0, 1, 2, 3, 10, 11, 12, 13, 14, 15, 4, 5, 6, 7, 8, 9, 22, 23, 24, 25, 26, 27, 16, 17, 18, 19, 20, 21]
+        pair = keypoint_pair + [v + kpt_num for v in paf_pair]
+        for i in range(len(pair)):
+            if i >= kpt_num and (i - kpt_num) % 2 == 0:
+                o[:, i] += f[:, pair[i]] * -1
+            else:
+                o[:, i] += f[:, pair[i]]
+        o[:, kpt_num:] *= 0.5
+        out["%s_hm2d_flipmerged" % bn] = o.numpy().copy()
+        out["%s_hm2d_flipraw" % bn] = f2d.numpy().copy()
+    np.savez_compressed(os.path.join(HERE, "backbone_64x96.npz"), **out)
+    print("backbone golden:", {k: v.shape for k, v in out.items()})
+
+
+def golden_lift():
+    np.int = int
+    np.float = float
+    os.environ.setdefault("PROJECT_HOME", "/tmp/smap_project_home")
+    ed = types.ModuleType("easydict")
+
+    class EasyDict(dict):
+        def __getattr__(self, k):
+            return self[k]
+
+        def __setattr__(self, k, v):
+            self[k] = v
+
+    ed.EasyDict = EasyDict
+    sys.modules["easydict"] = ed
+    import cv2
+    import test_util as T
+
+    from cases import N_LIFT_CASES, lift_case_inputs
+
+    cases = {}
+    for ci in range(N_LIFT_CASES):
+        b, det_d, root_d, (iw, ih) = lift_case_inputs(ci)
+        s = min(832 / iw, 512 / ih)
+        scale = {"scale": np.asarray(s), "img_width": np.asarray(iw), "img_height": np.asarray(ih),
+                 "net_width": np.asarray(832), "net_height": np.asarray(512)}
+        scale["f_x"] = scale["img_width"]
+        scale["f_y"] = scale["img_width"]
+        scale["cx"] = scale["img_width"] / 2
+        scale["cy"] = scale["img_height"] / 2
+        pb = torch.from_numpy(b.copy())
+        if len(pb) > 0:
+            pb[:, :, :2] *= 4  # test.py:117
+        pb = pb.numpy()
+        paf_up = cv2.resize(det_d.transpose(1, 2, 0), (832, 512), interpolation=cv2.INTER_NEAREST)  # test.py:123
+        rd_up = cv2.resize(root_d, (832, 512), interpolation=cv2.INTER_NEAREST)
+        pb = T.register_pred(pb, None)
+        if len(pb) == 0:
+            p2 = np.zeros((0, 15, 4), np.float32)
+            p3 = np.zeros((0, 15, 4), np.float64)
+            rdep = np.zeros((0,), np.float64)
+        else:
+            rdep = T.generate_relZ(pb, paf_up, rd_up, scale)
+            p3 = T.gen_3d_pose(pb, rdep, scale)
+            p2 = pb
+        cases["c%d_pred2d" % ci] = np.asarray(p2, np.float32)
+        cases["c%d_pred3d" % ci] = np.asarray(p3, np.float64)
+        cases["c%d_rootdepth" % ci] = np.asarray(rdep, np.float64)
+    small = cases
+    np.savez_compressed(os.path.join(HERE, "lift_cases.npz"), **small)
+    print("lift golden:", N_LIFT_CASES, "cases")
+
+
+if __name__ == "__main__":
+    golden_backbone()
+    golden_lift()
