@@ -1,0 +1,286 @@
+#!/usr/bin/env python
+"""bench.py - end-to-end FPS of the SMAP inference hot path (backbone + association + 3D lift) on B200.
+
+Contract (driver): `python bench.py --gpus N --steps K --warmup W [--impl reference]`, under torchrun for
+N > 1; one JSON line on stdout from rank 0.
+
+A "step" = one pass of the whole hot path over one batch of B synthetic 832x512 frames per GPU
+(BASELINE.json configs[1]: batch=8, 1xB200, full backbone + GPU association; for N > 1 each rank owns its own
+B frames and the per-image skeleton records are exchanged with ONE NCCL all-gather per step - weak scaling).
+
+  value : frames/s with the input batch already resident in HBM (smapb_infer_device + all-gather)
+  e2e   : frames/s through the C-ABI call with HOST buffers (smapb_infer_host: H2D of the frames from pinned
+          memory, the whole path, D2H of the skeleton records) + all-gather
+  roofline : the tensor-core convolution kernel (conv_tc_kernel, the dominant kernel): algorithmic conv FLOPs of
+          one step / summed CUDA-event time of its launches, against MEASURED_PEAKS.json bf16_tflops_sustained.
+          In bf16x3 mode every algorithmic FLOP is issued as 3 tensor-core FLOPs, so the tensor pipe runs at
+          3 x frac of the bf16 peak.
+  cpu_baseline : the CPU oracle of the same path (oracle/: PyTorch fp32 backbone on all cores + C++ association
+          + numpy lift) on a bounded sample of the same workload.
+`--impl reference` times that CPU oracle alone (the reference has no GPU-free path of its own for the association
+and /root/reference does not exist on the GPU box).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+IN_H, IN_W = 512, 832
+WORKLOAD = "configs[1]: batch=8 832x512 synthetic frames per GPU, random-init SMAP weights, full backbone + association + lift"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="smap_b200", choices=["smap_b200", "reference"])
+    ap.add_argument("--batch", type=int, default=8, help="frames per GPU per step")
+    ap.add_argument("--flip", type=int, default=0, help="flip-TTA (doubles the backbone work); BASELINE configs use 0")
+    ap.add_argument("--precision", default="bf16x3", choices=["bf16x3", "bf16"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-csv", default="")
+    return ap.parse_args()
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops_sustained", 1400.0), d.get("hbm_gbs", 6650.0), "measured"
+    return 1400.0, 6650.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu = gpu_index
+        self.samples, self.reasons = [], set()
+        self.max_mhz = None
+        self.stop_flag = False
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append(float(out[0]))
+                self.max_mhz = float(out[1])
+                for n, v in zip(names, out[2:]):
+                    if "Active" in v and "Not" not in v:
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            time.sleep(0.15)
+
+    def result(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU oracle legs (the only place bench.py touches oracle/)
+# ------------------------------------------------------------------------------------------------
+def cpu_oracle_fps(frames, threads=None, seed=1):
+    """Whole path on the host: oracle backbone (torch fp32) + C++ association + numpy lift."""
+    import torch
+
+    from oracle import assoc, lift_numpy, smap_torch
+
+    if threads:
+        torch.set_num_threads(threads)
+    sd = smap_torch.make_state_dict(0, "identity")
+    x = smap_torch.make_input(frames, IN_H, IN_W, seed=seed)
+    scale = lift_numpy.default_scale(1920, 1080)
+    assoc.lib()
+    t0 = time.perf_counter()
+    persons = 0
+    for i in range(frames):
+        hm, dd, rd = smap_torch.smap_forward(sd, x[i:i + 1])
+        smap_torch.rescale_reference_cuda(hm)
+        bodies = assoc.connect(hm[0].numpy(), rd[0, 0].numpy())
+        p2, p3, rdep = lift_numpy.lift(bodies, dd[0].numpy(), rd[0, 0].numpy(), scale)
+        persons += len(p2)
+    dt = time.perf_counter() - t0
+    return frames / dt, dt, torch.get_num_threads(), persons
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    frames_per_step = 1
+    for _ in range(max(1, min(args.warmup, 1))):
+        cpu_oracle_fps(1)
+    t0 = time.perf_counter()
+    threads = None
+    for s in range(args.steps):
+        fps, dt, threads, _ = cpu_oracle_fps(frames_per_step, seed=1 + s)
+    total = time.perf_counter() - t0
+    value = args.steps * frames_per_step / total
+    line = {
+        "impl": "reference", "metric": "end-to-end FPS @832x512 (backbone+association+lift)", "value": value,
+        "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "fp32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "frames_per_step": frames_per_step},
+        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": threads, "kind": "port",
+                         "sample": "%d frame(s) per step x %d steps, whole path on host cores" % (frames_per_step, args.steps)},
+        "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from smap_b200 import schema
+    from smap_b200.engine import RECORD_BYTES, Engine, scale_row
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    B = args.batch
+    eng = Engine(local, max_batch=B, in_h=IN_H, in_w=IN_W)
+    eng.load_state_dict(schema.make_state_dict(0, "identity"), precision=args.precision)
+    dev = torch.device("cuda", local)
+
+    # inputs: NROT distinct batches so that consecutive steps never re-read the same frames from L2
+    NROT = 4
+    host_batches = [schema.make_input(B, IN_H, IN_W, seed=1 + rank * 100 + r).pin_memory() for r in range(NROT)]
+    dev_batches = [hb.to(dev) for hb in host_batches]
+    sc = dict(scale=IN_W / 1920, img_width=1920, img_height=1080, net_width=IN_W, net_height=IN_H, f_x=1920.0,
+              f_y=1920.0, cx=960.0, cy=540.0)
+    scales_host = torch.from_numpy(np.stack([scale_row(sc)] * B)).pin_memory()
+    scales_dev = scales_host.to(dev)
+    gathered = torch.empty(world * B, RECORD_BYTES, dtype=torch.uint8, device=dev) if world > 1 else None
+    host_out = torch.empty(B, RECORD_BYTES, dtype=torch.uint8).pin_memory()
+
+    def step_device(i):
+        rec = eng.infer_device(dev_batches[i % NROT], scales_dev, do_flip=bool(args.flip))
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, rec)
+        return rec
+
+    def step_host(i):
+        recs = eng.infer_host(host_batches[i % NROT], scales_host, do_flip=bool(args.flip), out=host_out)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, torch.from_numpy(host_out.numpy()).to(dev, non_blocking=True))
+            torch.cuda.synchronize()
+        return recs
+
+    def timed(fn, steps):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms, wall * 1e3], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms, wall = t[0].item(), t[1].item() * 1e-3
+            dist.barrier()
+        return ms, wall
+
+    for i in range(max(3, args.warmup)):
+        step_device(i)
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = eng.launch_count()
+    ms_dev, wall_dev = timed(step_device, args.steps)
+    launches = eng.launch_count() - l0
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    for i in range(2):
+        step_host(i)
+    ms_host, wall_host = timed(step_host, args.steps)
+
+    # roofline leg: per-kernel CUDA-event timing of the same step (events on the launching stream)
+    n_conv, conv_flops = eng.plan_info(B)
+    prof_steps = min(args.steps, 5)
+    eng.profile_begin()
+    for i in range(prof_steps):
+        eng.infer_device(dev_batches[i % NROT], scales_dev, do_flip=bool(args.flip))
+    prof = eng.profile_end(args.profile_csv or None)
+    torch.cuda.synchronize()
+
+    if rank == 0:
+        peak_tf, peak_bw, peak_src = measured_peaks()
+        frames = world * B * args.steps
+        value = frames / (ms_dev * 1e-3)
+        e2e = frames / (wall_host)
+        conv_ms, conv_n = prof["conv"]
+        fwd = 2 if args.flip else 1
+        conv_ms_per_step = conv_ms / prof_steps
+        achieved = conv_flops * fwd / (conv_ms_per_step * 1e-3) * 1e-12 if conv_ms_per_step > 0 else 0.0
+        total_prof_ms = sum(v[0] for v in prof.values()) / prof_steps
+        line = {
+            "metric": "end-to-end FPS @832x512 (backbone+association+lift)", "value": value, "unit": "frames/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_dev / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16x3 (split-bf16 operands, fp32 accumulate; fp32-faithful)" if args.precision == "bf16x3" else "bf16",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD, "frames_per_gpu_per_step": B, "flip_tta": int(args.flip),
+                       "l2": "inputs rotate over %d distinct batches (%.0f MB) and every step streams >2 GB of activations (> 126 MB L2)"
+                             % (NROT, NROT * B * 3 * IN_H * IN_W * 4 / 1e6),
+                       "parallelism": "dp%d, one all-gather of skeleton records per step" % world},
+            "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": B * 3 * IN_H * IN_W * 4 + B * 9 * 8,
+                    "d2h_bytes_per_step": B * RECORD_BYTES, "ms_per_step": 1e3 * wall_host / args.steps},
+            "gpu_launches": int(launches),
+            "clocks": sampler.result(),
+            "roofline": {"bound": "tensor", "kernel": "conv_tc_kernel (%d launches/step)" % (conv_n // prof_steps),
+                         "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
+                         "peak_source": peak_src + " bf16_tflops_sustained",
+                         "algorithmic_gflop_per_step": conv_flops * fwd * 1e-9,
+                         "tensor_pipe_flop_multiplier": 3 if args.precision == "bf16x3" else 1,
+                         "kernel_ms_per_step": conv_ms_per_step, "share_of_step": conv_ms_per_step / total_prof_ms,
+                         "traffic": None},
+            "breakdown_ms_per_step": {k: v[0] / prof_steps for k, v in prof.items() if v[1]},
+        }
+        if not args.no_cpu_baseline:
+            fps, dt, threads, persons = cpu_oracle_fps(4)
+            line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
+                                    "sample": "4 frames of the same workload, whole path (oracle/: torch fp32 backbone on %d threads + "
+                                              "single-thread C++ association + numpy lift), %.1f s" % (threads, dt)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    eng.close()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -107,6 +107,13 @@ int smapb_infer_host(smapb_handle* h, const float* imgs_nchw_host, const double*
 /* ---- introspection ----------------------------------------------------------------------------- */
 /* number of kernels launched by this handle since creation */
 int64_t smapb_launch_count(const smapb_handle* h);
+/* Per-op device timing with CUDA events on the launching stream (bench.py roofline leg).  After
+ * smapb_profile_begin every kernel launched through this handle is bracketed by events; smapb_profile_end
+ * synchronises the device, sums milliseconds and launch counts per kind
+ * (0 conv_tc, 1 stem+maxpool, 2 other backbone elementwise, 3 association, 4 lift, 5 unused) into the two
+ * 6-element arrays and, if csv_path is not NULL, writes one line per launch. */
+int smapb_profile_begin(smapb_handle* h);
+int smapb_profile_end(smapb_handle* h, double* ms_by_kind, int* launches_by_kind, const char* csv_path);
 /* conv plan: number of tensor-core conv launches per forward and their algorithmic FLOPs (2*MACs, 1x) */
 int smapb_plan_info(const smapb_handle* h, int B, int* n_conv_launches, double* conv_flops);
 /* Run one standalone convolution through the tensor-core path (test/bench hook).

@@ -1,4 +1,4 @@
-"""ORACLE - TEST INFRASTRUCTURE ONLY.  ctypes front-end of oracle/assoc_oracle.c
+"""ORACLE - TEST INFRASTRUCTURE ONLY.  ctypes front-end of oracle/assoc_oracle.cpp
 (the CPU restatement of dapalib.extract/connect)."""
 import ctypes
 import os
@@ -13,9 +13,9 @@ _lib = None
 
 
 def build(force=False):
-    src = os.path.join(HERE, "assoc_oracle.c")
+    src = os.path.join(HERE, "assoc_oracle.cpp")
     if force or not os.path.exists(SO) or os.path.getmtime(SO) < os.path.getmtime(src):
-        subprocess.check_call(["gcc", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-o", SO, src, "-lm"])
+        subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-o", SO, src, "-lm"])
     return SO
 
 
@@ -31,6 +31,7 @@ def lib():
         _lib.oracle_group.restype = ctypes.c_int
         _lib.oracle_connect.argtypes = [fp, fp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, fp, fp, fp]
         _lib.oracle_connect.restype = ctypes.c_int
+        _lib.oracle_depth_order.argtypes = [fp, ctypes.c_int, ctypes.POINTER(ctypes.c_int)]
     return _lib
 
 
@@ -61,3 +62,11 @@ def connect(hms, rdepth, root_idx=2, dist_flag=True, return_all=False):
     if return_all:
         return bodies[:P].copy(), peaks, scores
     return bodies[:P].copy()
+
+
+def depth_order(depth):
+    """association.cpp:144 alone: indices of the (unstable, std::sort) ascending depth sort."""
+    d = np.ascontiguousarray(depth, np.float32)
+    order = np.zeros(len(d), np.int32)
+    lib().oracle_depth_order(_p(d), len(d), order.ctypes.data_as(ctypes.POINTER(ctypes.c_int)))
+    return order

@@ -1,7 +1,7 @@
 /*
  * ORACLE - TEST INFRASTRUCTURE ONLY.  Not part of the product path.
  *
- * CPU restatement (plain C, fp32 with pinned FMA placement) of the SMAP
+ * CPU restatement (C-style C++, fp32 with pinned FMA placement) of the SMAP
  * depth-aware part association.  Only tests/, __graft_entry__.smoke() and
  * bench.py's cpu_baseline / --impl reference legs may load this library.
  *
@@ -28,6 +28,10 @@
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
+
+#include <algorithm>
+
+extern "C" {
 
 #define NJ 15
 #define NL 14
@@ -181,21 +185,27 @@ int oracle_group(const float* peaks, const float* scores, const float* rdepth, i
         depth[i] = rdepth[yy * w + xx];
         order[i] = i;
     }
-    /* association.cpp:144 ascending sort; ties keep index order (stable insertion sort) */
-    for (int i = 1; i < P; i++) {
-        const int oi = order[i];
-        const float di = depth[oi];
-        int j = i - 1;
-        while (j >= 0 && depth[order[j]] > di) {
-            order[j + 1] = order[j];
-            j--;
+    /* association.cpp:144 `predRootDepth.sort(0, false)`: at::sort with stable=false on a CPU tensor is
+     * std::sort over (key, index) pairs with the comparator below (ATen SortingKernel.cpp, KeyValueCompAsc).
+     * It is NOT stable; the order of equal depths is whatever libstdc++'s introsort leaves, which is
+     * deterministic and is verified against torch.sort in tests/test_oracle_assoc.py. */
+    {
+        struct KV {
+            float k;
+            int v;
+        };
+        KV kv[MAXP];
+        for (int i = 0; i < P; i++) {
+            kv[i].k = depth[i];
+            kv[i].v = i;
         }
-        order[j + 1] = oi;
+        std::sort(kv, kv + P, [](const KV& a, const KV& b) { return (!std::isnan(a.k) && std::isnan(b.k)) || (a.k < b.k); });
+        for (int i = 0; i < P; i++) order[i] = kv[i].v;
     }
     float sortDepth[MAXP];
     for (int i = 0; i < P; i++) sortDepth[i] = depth[order[i]];
 
-    static int remap[NJ][MAXP]; /* association.cpp:148-154 */
+    int remap[NJ][MAXP]; /* association.cpp:148-154 */
     for (int j = 0; j < NJ; j++)
         for (int p = 0; p < P; p++) remap[j][p] = (j == rootIdx) ? order[p] : p;
 
@@ -271,3 +281,21 @@ int oracle_connect(const float* hms, const float* rdepth, int h, int w, int root
     oracle_paf(hms, h, w, peaks, scores);
     return oracle_group(peaks, scores, rdepth, h, w, rootIdx, distFlag, bodies);
 }
+
+/* test hook: the sort of association.cpp:144 alone (order[i] = index of the i-th smallest depth) */
+void oracle_depth_order(const float* depth, int n, int* order) {
+    struct KV {
+        float k;
+        int v;
+    };
+    KV* kv = new KV[n];
+    for (int i = 0; i < n; i++) {
+        kv[i].k = depth[i];
+        kv[i].v = i;
+    }
+    std::sort(kv, kv + n, [](const KV& a, const KV& b) { return (!std::isnan(a.k) && std::isnan(b.k)) || (a.k < b.k); });
+    for (int i = 0; i < n; i++) order[i] = kv[i].v;
+    delete[] kv;
+}
+
+} /* extern "C" */

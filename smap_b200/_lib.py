@@ -13,7 +13,7 @@ EXPORTS = [
     "smapb_create", "smapb_destroy", "smapb_last_error", "smapb_version", "smapb_load_weight",
     "smapb_finalize_weights", "smapb_backbone_forward", "smapb_merge_scale", "smapb_assoc_extract",
     "smapb_assoc_connect", "smapb_lift3d", "smapb_infer_device", "smapb_infer_host", "smapb_launch_count",
-    "smapb_plan_info", "smapb_conv_test",
+    "smapb_plan_info", "smapb_conv_test", "smapb_profile_begin", "smapb_profile_end",
 ]
 
 _lib = None
@@ -53,6 +53,8 @@ def load():
     lib.smapb_infer_host.argtypes = [vp, vp, vp, i32, i32, vp, vp]
     lib.smapb_launch_count.argtypes = [vp]
     lib.smapb_launch_count.restype = i64
+    lib.smapb_profile_begin.argtypes = [vp]
+    lib.smapb_profile_end.argtypes = [vp, c.POINTER(c.c_double), c.POINTER(i32), c.c_char_p]
     lib.smapb_plan_info.argtypes = [vp, i32, c.POINTER(i32), c.POINTER(c.c_double)]
     lib.smapb_conv_test.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp,
                                     c.POINTER(c.c_float), vp]

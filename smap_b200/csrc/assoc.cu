@@ -234,6 +234,142 @@ paf_kernel(const float* __restrict__ hms, int nchan, int h, int w, const float* 
 }
 
 // ---------------------------------------------------------------------------------------------
+// `predRootDepth.sort(0, false)` (association.cpp:144): at::sort(stable=false) on a CPU tensor is libstdc++
+// std::sort over (key, index) pairs with comp(a,b) = (!isnan(a) && isnan(b)) || a < b.  It is not stable, so
+// equal depths come out in introsort order.  When all depths are distinct the order is unique and a parallel
+// rank sort is used; otherwise one thread replays libstdc++'s algorithm (bits/stl_algo.h: introsort loop with
+// median-of-3 to first + unguarded partition, threshold 16, heap-sort fallback at depth 2*floor(log2 n), final
+// insertion sort) step by step so that the tie order is bit-identical to the reference.
+// ---------------------------------------------------------------------------------------------
+struct KV {
+    float k;
+    int v;
+};
+__device__ __forceinline__ bool kv_comp(const KV& a, const KV& b) { return (!isnan(a.k) && isnan(b.k)) || (a.k < b.k); }
+__device__ __forceinline__ void kv_swap(KV& a, KV& b) {
+    const KV t = a;
+    a = b;
+    b = t;
+}
+__device__ void kv_adjust_heap(KV* first, int hole, int len, KV value) {  // std::__adjust_heap + __push_heap
+    const int top = hole;
+    int child = hole;
+    while (child < (len - 1) / 2) {
+        child = 2 * (child + 1);
+        if (kv_comp(first[child], first[child - 1])) child--;
+        first[hole] = first[child];
+        hole = child;
+    }
+    if ((len & 1) == 0 && child == (len - 2) / 2) {
+        child = 2 * (child + 1);
+        first[hole] = first[child - 1];
+        hole = child - 1;
+    }
+    int parent = (hole - 1) / 2;
+    while (hole > top && kv_comp(first[parent], value)) {
+        first[hole] = first[parent];
+        hole = parent;
+        parent = (hole - 1) / 2;
+    }
+    first[hole] = value;
+}
+__device__ void kv_heap_sort(KV* first, int len) {  // std::__partial_sort(first, last, last)
+    if (len >= 2) {                                  // __make_heap
+        int parent = (len - 2) / 2;
+        while (true) {
+            const KV value = first[parent];
+            kv_adjust_heap(first, parent, len, value);
+            if (parent == 0) break;
+            parent--;
+        }
+    }
+    // __heap_select(first, last, last) has an empty tail; then __sort_heap
+    for (int last = len; last > 1;) {
+        --last;
+        const KV value = first[last];  // __pop_heap(first, last, last)
+        first[last] = first[0];
+        kv_adjust_heap(first, 0, last, value);
+    }
+}
+__device__ __forceinline__ void kv_unguarded_linear_insert(KV* a, int last) {
+    const KV val = a[last];
+    int next = last - 1;
+    while (kv_comp(val, a[next])) {
+        a[last] = a[next];
+        last = next;
+        --next;
+    }
+    a[last] = val;
+}
+__device__ void kv_insertion_sort(KV* a, int first, int last) {
+    if (first == last) return;
+    for (int i = first + 1; i != last; ++i) {
+        if (kv_comp(a[i], a[first])) {
+            const KV val = a[i];
+            for (int j = i; j > first; --j) a[j] = a[j - 1];
+            a[first] = val;
+        } else {
+            kv_unguarded_linear_insert(a, i);
+        }
+    }
+}
+__device__ void kv_std_sort(KV* a, int n) {
+    if (n <= 0) return;
+    int lg = 0;
+    while ((1 << (lg + 1)) <= n) lg++;
+    // explicit stack for the recursive half of __introsort_loop
+    int st_first[32], st_last[32], st_depth[32];
+    int sp = 0;
+    st_first[0] = 0, st_last[0] = n, st_depth[0] = 2 * lg;
+    sp = 1;
+    while (sp > 0) {
+        --sp;
+        int first = st_first[sp], last = st_last[sp], depth = st_depth[sp];
+        while (last - first > 16) {
+            if (depth == 0) {
+                kv_heap_sort(a + first, last - first);
+                break;
+            }
+            --depth;
+            // __unguarded_partition_pivot
+            const int mid = first + (last - first) / 2;
+            {
+                const int ia = first + 1, ib = mid, ic = last - 1;
+                if (kv_comp(a[ia], a[ib])) {
+                    if (kv_comp(a[ib], a[ic])) kv_swap(a[first], a[ib]);
+                    else if (kv_comp(a[ia], a[ic])) kv_swap(a[first], a[ic]);
+                    else kv_swap(a[first], a[ia]);
+                } else if (kv_comp(a[ia], a[ic])) kv_swap(a[first], a[ia]);
+                else if (kv_comp(a[ib], a[ic])) kv_swap(a[first], a[ic]);
+                else kv_swap(a[first], a[ib]);
+            }
+            int lo = first + 1, hi = last;
+            while (true) {
+                while (kv_comp(a[lo], a[first])) ++lo;
+                --hi;
+                while (kv_comp(a[first], a[hi])) --hi;
+                if (!(lo < hi)) break;
+                kv_swap(a[lo], a[hi]);
+                ++lo;
+            }
+            const int cut = lo;
+            // recurse on [cut, last), iterate on [first, cut): libstdc++ runs the right part first, but the two
+            // ranges are disjoint, so the order of processing does not change the result
+            st_first[sp] = cut, st_last[sp] = last, st_depth[sp] = depth;
+            ++sp;
+            last = cut;
+        }
+    }
+    // __final_insertion_sort
+    if (n > 16) {
+        kv_insertion_sort(a, 0, 16);
+        for (int i = 16; i != n; ++i) kv_unguarded_linear_insert(a, i);
+    } else {
+        kv_insertion_sort(a, 0, n);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Grouping: one CTA (5 warps) per image.  The 14 limbs form 5 independent chains hanging off the
 // pelvis/neck (dst joints are disjoint, `used` is per limb), so the sequential reference order
 //   1,0,2,3,...,13  (association.cpp:164-170)
@@ -254,6 +390,8 @@ group_kernel(const float* __restrict__ peaks, const float* __restrict__ scores, 
     __shared__ float s_depth[MAXP + 1];
     __shared__ float s_sorted[MAXP + 1];
     __shared__ int s_order[MAXP + 1];
+    __shared__ int s_rank[MAXP + 1];
+    __shared__ unsigned long long s_kv[MAXP + 1];
     __shared__ unsigned char s_remap[NJ][MAXP + 1];
     __shared__ float s_body[MAXP][NJ][3];  // x, y, score
     __shared__ unsigned char s_used[GROUP_WARPS][MAXP + 1];
@@ -277,16 +415,38 @@ group_kernel(const float* __restrict__ peaks, const float* __restrict__ scores, 
         s_depth[i] = rd[min(h - 1, max(0, yy)) * w + min(w - 1, max(0, xx))];
     }
     __syncthreads();
-    // stable ascending rank sort (association.cpp:144)
-    for (int i = tid; i < P; i += nthr) {
-        const float di = s_depth[i];
-        int r = 0;
-        for (int j = 0; j < P; j++) {
-            const float dj = s_depth[j];
-            r += (dj < di) || (dj == di && j < i);
+    // ascending depth order (association.cpp:144): unique keys -> parallel rank sort, ties/NaNs -> std::sort replay
+    {
+        int tie = 0;
+        for (int i = tid; i < P; i += nthr) {
+            const KV a = {s_depth[i], i};
+            int r = 0;
+            for (int j = 0; j < P; j++) {
+                const KV b = {s_depth[j], j};
+                const bool lt = kv_comp(b, a);
+                r += lt;
+                tie |= (j != i) && !lt && !kv_comp(a, b);
+            }
+            s_rank[i] = r;
         }
-        s_order[r] = i;
-        s_sorted[r] = di;
+        const int any_tie = __syncthreads_or(tie);
+        if (!any_tie) {
+            for (int i = tid; i < P; i += nthr) {
+                s_order[s_rank[i]] = i;
+                s_sorted[s_rank[i]] = s_depth[i];
+            }
+        } else if (tid == 0) {
+            KV* kv = reinterpret_cast<KV*>(s_kv);
+            for (int i = 0; i < P; i++) {
+                kv[i].k = s_depth[i];
+                kv[i].v = i;
+            }
+            kv_std_sort(kv, P);
+            for (int i = 0; i < P; i++) {
+                s_order[i] = kv[i].v;
+                s_sorted[i] = kv[i].k;
+            }
+        }
     }
     __syncthreads();
     for (int i = tid; i < NJ * P; i += nthr) {  // association.cpp:148-154

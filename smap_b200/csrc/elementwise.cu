@@ -339,7 +339,9 @@ __global__ void merge_scale_kernel(float* __restrict__ hm, const float* __restri
                 v = __fadd_rn(v, f);                    // test.py:68
             if (c >= 15) v = __fmul_rn(v, 0.5f);        // test.py:69 (key-point maps are summed, not averaged)
         }
-        if (do_scale) v = (c < 15) ? __fdiv_rn(v, 255.f) : __fdiv_rn(v, 127.f);  // test.py:111-112 (true division)
+        // test.py:111-112 `hmsIn[:15] /= 255; hmsIn[15:] /= 127` on a CUDA tensor: ATen's CUDA true-divide by a CPU
+        // scalar multiplies by the fp32 reciprocal (BinaryDivTrueKernel.cu), it is not an IEEE division.
+        if (do_scale) v = (c < 15) ? __fmul_rn(v, __fdiv_rn(1.f, 255.f)) : __fmul_rn(v, __fdiv_rn(1.f, 127.f));
         hm[i] = v;
     }
     pdl_trigger();

@@ -129,6 +129,13 @@ struct smapb_handle {
     double* scales_dev = nullptr;
     smapb_record* records_dev = nullptr;
     bool use_graph = true;
+    // profiling (per-op CUDA events on the launching stream)
+    bool profiling = false;
+    std::vector<cudaEvent_t> prof_events;
+    std::vector<int> prof_kind;          // kind of the op that ended at event i (-1 = interval start)
+    std::vector<std::string> prof_desc;  // description of that op
+    std::vector<double> prof_flops;
+    size_t prof_used = 0;
 };
 
 namespace {
@@ -143,6 +150,24 @@ int fail(smapb_handle* h, int code, const std::string& msg) {
         if (e_ != cudaSuccess)                                                                            \
             return fail(h, -10, std::string(#call) + ": " + cudaGetErrorString(e_) + " @" + std::to_string(__LINE__)); \
     } while (0)
+
+enum ProfKind { PK_START = -1, PK_CONV = 0, PK_STEM = 1, PK_ELEM = 2, PK_ASSOC = 3, PK_LIFT = 4, PK_COPY = 5 };
+void prof_mark(smapb_handle* h, int kind, cudaStream_t st, const char* desc = "", double flops = 0) {
+    if (!h->profiling) return;
+    if (h->prof_used == h->prof_events.size()) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        h->prof_events.push_back(e);
+        h->prof_kind.push_back(0);
+        h->prof_desc.emplace_back();
+        h->prof_flops.push_back(0);
+    }
+    cudaEventRecord(h->prof_events[h->prof_used], st);
+    h->prof_kind[h->prof_used] = kind;
+    h->prof_desc[h->prof_used] = desc;
+    h->prof_flops[h->prof_used] = flops;
+    h->prof_used++;
+}
 
 template <typename T>
 int dev_alloc(smapb_handle* h, T** p, size_t count) {
@@ -577,25 +602,36 @@ int run_plan(smapb_handle* h, Plan* plan, const float* imgs, float* hm2d, float*
              cudaStream_t st) {
     const int B = plan->B;
     const int T = h->planes;
+    prof_mark(h, PK_START, st);
     for (const Op& op : plan->ops) {
         switch (op.kind) {
             case OP_STEM:
                 CK(launch_stem(imgs, h->stem_w, h->stem_b, B, h->in_h, h->in_w, op.out.ptr, op.out.plane(), T, st));
+                prof_mark(h, PK_STEM, st, "stem7x7");
                 break;
             case OP_MAXPOOL:
                 CK(launch_maxpool(op.a.ptr, op.a.plane(), B, op.a.H, op.a.W, op.a.C, op.out.ptr, op.out.plane(), T, st));
+                prof_mark(h, PK_STEM, st, "maxpool");
                 break;
             case OP_CONV:
                 CK(launch_conv(op.cp, op.block_n, h->nterms, h->sm_count, st, false));
+                if (h->profiling) {
+                    char d[160];
+                    snprintf(d, sizeof d, "conv k%d s%d cin%d cout%d out%dx%d bn%d tiles%d", op.cp.ksize, op.cp.stride,
+                             op.cp.kchunks * 64, op.cp.Cout, op.cp.Hout, op.cp.Wout, op.block_n, op.cp.total_tiles);
+                    prof_mark(h, PK_CONV, st, d, op.flops);
+                }
                 break;
             case OP_UPADD:
                 CK(launch_upadd_relu(op.a.ptr, op.a.plane(), op.b.ptr, op.b.plane(), B, op.a.H, op.a.W, op.b.H, op.b.W,
                                      op.a.C, op.out.ptr, op.out.plane(), T, st));
+                prof_mark(h, PK_ELEM, st, "upadd_relu");
                 break;
             case OP_HEADMERGE: {
                 float* dst = op.which_out == 0 ? hm2d : op.which_out == 1 ? detd : rootd;
                 CK(launch_head_merge(op.f4.ptr, op.f3.ptr, op.f2.ptr, B, op.f4.H, op.f4.W, op.f3.H, op.f3.W, op.f2.H,
                                      op.f2.W, op.f4.C, op.cout, dst, st));
+                prof_mark(h, PK_ELEM, st, "head_merge");
                 break;
             }
         }
@@ -883,14 +919,19 @@ int smapb_infer_device(smapb_handle* h, const float* imgs, const double* scales,
         }
         flip_w_kernel<<<148 * 8, 256, 0, st>>>(imgs, h->imgs_flip, (long long)B * 3 * h->in_h, h->in_w);
         CK(cudaGetLastError());
+        prof_mark(h, PK_ELEM, st, "flip_w");
         h->launches++;
         rc = run_plan(h, plan, h->imgs_flip, h->hm_flip, h->scratch_detd, h->scratch_rootd, st);
         if (rc) return rc;
     }
     CK(launch_merge_scale(h->hm, do_flip ? h->hm_flip : nullptr, B, h->h, h->w, 1, st));
+    prof_mark(h, PK_ELEM, st, "merge_scale");
     CK(launch_nms(h->hm, NC2D, B, h->h, h->w, 0.2f, h->peaks, st));
+    prof_mark(h, PK_ASSOC, st, "nms");
     CK(launch_paf(h->hm, NC2D, B, h->h, h->w, h->peaks, h->scores, 0, st));
+    prof_mark(h, PK_ASSOC, st, "paf");
     CK(launch_group(h->peaks, h->scores, h->rootd, B, h->h, h->w, 2, 1, h->bodies, h->counts, st));
+    prof_mark(h, PK_ASSOC, st, "group");
     char* rb = reinterpret_cast<char*>(records);
     CK(launch_lift(h->bodies, h->counts, h->detd, h->rootd, scales, B, h->h, h->w, 2,
                    reinterpret_cast<float*>(rb + offsetof(smapb_record, pred2d)),
@@ -898,6 +939,7 @@ int smapb_infer_device(smapb_handle* h, const float* imgs, const double* scales,
                    reinterpret_cast<double*>(rb + offsetof(smapb_record, root_depth)),
                    reinterpret_cast<int*>(rb + offsetof(smapb_record, count)), sizeof(smapb_record) / 4,
                    sizeof(smapb_record) / 8, sizeof(smapb_record) / 8, sizeof(smapb_record) / 4, st));
+    prof_mark(h, PK_LIFT, st, "lift");
     h->launches += 5;
     return 0;
 }
@@ -918,6 +960,40 @@ int smapb_infer_host(smapb_handle* h, const float* imgs_host, const double* scal
 }
 
 int64_t smapb_launch_count(const smapb_handle* h) { return h ? h->launches : 0; }
+
+int smapb_profile_begin(smapb_handle* h) {
+    if (!h) return -1;
+    h->profiling = true;
+    h->prof_used = 0;
+    return 0;
+}
+
+int smapb_profile_end(smapb_handle* h, double* ms_by_kind, int* launches_by_kind, const char* csv_path) {
+    if (!h) return -1;
+    cudaSetDevice(h->device);
+    h->profiling = false;
+    CK(cudaDeviceSynchronize());
+    for (int k = 0; k < 6; k++) {
+        if (ms_by_kind) ms_by_kind[k] = 0;
+        if (launches_by_kind) launches_by_kind[k] = 0;
+    }
+    FILE* f = csv_path ? fopen(csv_path, "w") : nullptr;
+    if (f) fprintf(f, "idx,kind,ms,gflop,tflops,desc\n");
+    for (size_t i = 1; i < h->prof_used; i++) {
+        const int k = h->prof_kind[i];
+        if (k < 0) continue;
+        float ms = 0;
+        cudaEventElapsedTime(&ms, h->prof_events[i - 1], h->prof_events[i]);
+        if (ms_by_kind) ms_by_kind[k] += ms;
+        if (launches_by_kind) launches_by_kind[k]++;
+        if (f)
+            fprintf(f, "%zu,%d,%.5f,%.4f,%.2f,%s\n", i, k, ms, h->prof_flops[i] * 1e-9,
+                    ms > 0 ? h->prof_flops[i] / (ms * 1e-3) * 1e-12 : 0.0, h->prof_desc[i].c_str());
+    }
+    if (f) fclose(f);
+    h->prof_used = 0;
+    return 0;
+}
 
 int smapb_plan_info(const smapb_handle* hc, int B, int* n_conv, double* conv_flops) {
     smapb_handle* h = const_cast<smapb_handle*>(hc);

@@ -154,6 +154,17 @@ class Engine:
     def launch_count(self):
         return int(self.lib.smapb_launch_count(self._h))
 
+    def profile_begin(self):
+        self._check(self.lib.smapb_profile_begin(self._h), "smapb_profile_begin")
+
+    def profile_end(self, csv_path=None):
+        """-> dict kind -> (ms, launches); kinds: conv, stem, elementwise, assoc, lift."""
+        ms = (ctypes.c_double * 6)()
+        n = (ctypes.c_int * 6)()
+        self._check(self.lib.smapb_profile_end(self._h, ms, n, csv_path.encode() if csv_path else None), "smapb_profile_end")
+        names = ["conv", "stem", "elementwise", "assoc", "lift", "other"]
+        return {names[i]: (ms[i], n[i]) for i in range(6)}
+
     def plan_info(self, B):
         n = ctypes.c_int()
         f = ctypes.c_double()

@@ -1,0 +1,67 @@
+"""GPU: the tcgen05 implicit-GEMM convolution against a plain PyTorch fp32 reference of the same op
+(TF32 disabled).  Tolerance for the bf16x3 (split-bf16, fp32-faithful) mode: 2e-5 of the output max."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from smap_b200.engine import Engine
+
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    e = Engine(0, max_batch=2, in_h=64, in_w=96)
+    yield e
+    e.close()
+
+
+CASES = [
+    # B, H, W, Cin, Cout, k, stride, relu, res
+    (1, 16, 24, 64, 64, 1, 1, True, False),      # flat 1x1, single k-block
+    (2, 16, 26, 256, 64, 1, 1, True, False),     # flat 1x1, ragged M (832 rows)
+    (1, 16, 24, 64, 256, 1, 1, False, True),     # residual epilogue, N=256
+    (2, 32, 52, 128, 128, 3, 1, True, False),    # 3x3 s1, patch tiles, padding via TMA OOB
+    (1, 16, 26, 512, 512, 3, 1, True, False),    # 3x3 s1 on the 16x26 level (non power-of-two width)
+    (2, 32, 52, 128, 128, 3, 2, True, False),    # 3x3 stride 2 (TMA elementStrides)
+    (1, 64, 104, 256, 512, 1, 2, False, False),  # 1x1 stride 2 (downsample branch)
+    (1, 32, 52, 256, 43, 3, 1, False, False),    # thin head, Cout padded to 64
+    (1, 32, 52, 256, 14, 3, 1, False, False),    # thin head, Cout padded to 32
+    (1, 16, 24, 256, 1, 3, 1, False, False),     # root-depth head
+    (2, 16, 26, 2048, 512, 1, 1, True, False),   # long K (32 k-blocks): ring wrap-around
+]
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_conv_bf16x3_matches_fp32(eng, case):
+    B, H, W, Cin, Cout, k, stride, relu, use_res = case
+    g = torch.Generator(device="cpu").manual_seed(hash(case) % (2 ** 31))
+    x = torch.randn(B, H, W, Cin, generator=g).cuda()
+    w = (torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5).cuda()
+    b = torch.randn(Cout, generator=g).cuda()
+    pad = k // 2
+    ref = F.conv2d(x.permute(0, 3, 1, 2), w, b, stride=stride, padding=pad)
+    res = None
+    if use_res:
+        res = torch.randn(B, ref.shape[2], ref.shape[3], Cout, generator=g).cuda()
+        ref = ref + res.permute(0, 3, 1, 2)
+    if relu:
+        ref = F.relu(ref)
+    y = eng.conv_test(x, w, b, res=res, stride=stride, relu=relu)
+    torch.cuda.synchronize()
+    ref = ref.permute(0, 2, 3, 1)
+    err = (y - ref).abs().max().item() / ref.abs().max().item()
+    assert err < 2e-5, "relative error %g" % err
+
+
+def test_conv_bf16_fast_mode_is_coarser_but_sane(eng):
+    g = torch.Generator(device="cpu").manual_seed(0)
+    x = torch.randn(1, 16, 24, 128, generator=g).cuda()
+    w = (torch.randn(128, 128, 3, 3, generator=g) / (128 * 9) ** 0.5).cuda()
+    b = torch.zeros(128).cuda()
+    ref = F.conv2d(x.permute(0, 3, 1, 2), w, b, padding=1).permute(0, 2, 3, 1)
+    y = eng.conv_test(x, w, b, relu=False, precision="bf16")
+    err = (y - ref).abs().max().item() / ref.abs().max().item()
+    assert err < 2e-2

@@ -1,4 +1,4 @@
-"""CPU: known-answer tests of the association oracle (oracle/assoc_oracle.c), covering every branch the
+"""CPU: known-answer tests of the association oracle (oracle/assoc_oracle.cpp), covering every branch the
 reference has (nmsBase.cu:24-49,84-133; bodyPartConnectorBase.cu:23-62; association.cpp:133-136,185,190,202-228).
 The reference ships no vectors for this path; on the GPU box the oracle itself is pinned against the unmodified
 reference extension (tests/test_assoc_gpu.py)."""
@@ -137,3 +137,17 @@ def test_connect_deterministic(seed):
     a = assoc.connect(s["hms"], s["root_d"])
     b = assoc.connect(s["hms"], s["root_d"])
     assert np.array_equal(a, b)
+
+
+def test_depth_sort_matches_torch_unstable_sort():
+    """association.cpp:144 is an UNSTABLE at::sort; the oracle replays it with std::sort (same algorithm)."""
+    import torch
+
+    rng = np.random.default_rng(1)
+    for t in range(300):
+        n = int(rng.integers(1, 128))
+        k = rng.integers(0, max(2, n // 3), n).astype(np.float32)  # many ties
+        if t % 7 == 0:
+            k[rng.integers(0, n)] = np.nan
+        _, idx = torch.from_numpy(k.copy()).sort(0, False)
+        assert np.array_equal(assoc.depth_order(k), idx.numpy())

@@ -1,0 +1,64 @@
+"""GPU: the whole path through the C ABI (smapb_infer_device / smapb_infer_host) against the oracle chain."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import assoc, lift_numpy, smap_torch
+from smap_b200 import schema
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from smap_b200.engine import Engine
+
+    e = Engine(0, max_batch=3, in_h=512, in_w=832)
+    e.load_state_dict(schema.make_state_dict(0, "identity"))
+    yield e
+    e.close()
+
+
+def oracle_chain(hm, dd, rd, sc):
+    """hm (already merged, unscaled) -> reference-order association + lift on the host."""
+    hm = smap_torch.rescale_reference_cuda(hm.clone())
+    out = []
+    for i in range(hm.shape[0]):
+        bodies = assoc.connect(hm[i].cpu().numpy(), rd[i, 0].cpu().numpy())
+        out.append(lift_numpy.lift(bodies, dd[i].cpu().numpy(), rd[i, 0].cpu().numpy(), sc))
+    return out
+
+
+@pytest.mark.parametrize("flip", [False, True])
+def test_infer_device_matches_oracle_chain(eng, flip):
+    from smap_b200.engine import records_to_numpy, scale_row
+
+    x = schema.make_input(3, 512, 832, seed=21).cuda()
+    sc = lift_numpy.default_scale(1920, 1080)
+    scales = torch.from_numpy(np.stack([scale_row(sc)] * 3)).cuda()
+    rec = records_to_numpy(eng.infer_device(x, scales, do_flip=flip))
+    hm, dd, rd = eng.forward(x)
+    if flip:
+        hm_f, _, _ = eng.forward(torch.flip(x, [-1]))
+        hm = smap_torch.flip_merge(hm.clone(), hm_f)  # reference merge loop (test.py:55-70) on our tensors
+    torch.cuda.synchronize()
+    ref = oracle_chain(hm, dd, rd, sc)
+    for i, (p2, p3, rdep) in enumerate(ref):
+        n = int(rec["count"][i])
+        assert n == len(p2)
+        assert np.array_equal(rec["pred2d"][i, :n], p2)
+        assert np.array_equal(rec["root_depth"][i, :n], rdep)
+        np.testing.assert_allclose(rec["pred3d"][i, :n], p3, rtol=1e-12, atol=1e-12)
+        assert not rec["pred3d"][i, n:].any()
+
+
+def test_infer_host_equals_infer_device(eng):
+    from smap_b200.engine import records_to_numpy, scale_row
+
+    x = schema.make_input(2, 512, 832, seed=22)
+    sc = lift_numpy.default_scale(640, 480)
+    scales = np.stack([scale_row(sc)] * 2)
+    a = eng.infer_host(x.pin_memory(), scales)
+    b = records_to_numpy(eng.infer_device(x.cuda(), torch.from_numpy(scales).cuda()))
+    assert a.tobytes() == b.tobytes()
+    assert eng.launch_count() > 0
