@@ -118,10 +118,11 @@ int smapb_profile_end(smapb_handle* h, double* ms_by_kind, int* launches_by_kind
 int smapb_plan_info(const smapb_handle* h, int B, int* n_conv_launches, double* conv_flops);
 /* Run one standalone convolution through the tensor-core path (test/bench hook).
  * x: fp32 NHWC [B,H,W,Cin]; w: fp32 [Cout,Cin,k,k]; bias fp32 [Cout]; res (optional) fp32 NHWC of the
- * output shape added before the ReLU; y: fp32 NHWC [B,Ho,Wo,Cout].  All device pointers. */
+ * output shape added before the ReLU; post1/post2 (optional) fp32 NHWC added after the ReLU (in that order);
+ * y: fp32 NHWC [B,Ho,Wo,Cout].  All device pointers. */
 int smapb_conv_test(smapb_handle* h, const float* x_dev, const float* w_dev, const float* bias_dev,
-                    const float* res_dev, int B, int H, int W, int Cin, int Cout, int k, int stride, int relu,
-                    int precision, float* y_dev, float* ms_out, void* stream);
+                    const float* res_dev, const float* post1_dev, const float* post2_dev, int B, int H, int W, int Cin,
+                    int Cout, int k, int stride, int relu, int precision, float* y_dev, float* ms_out, void* stream);
 
 #ifdef __cplusplus
 }

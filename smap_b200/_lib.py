@@ -56,7 +56,7 @@ def load():
     lib.smapb_profile_begin.argtypes = [vp]
     lib.smapb_profile_end.argtypes = [vp, c.POINTER(c.c_double), c.POINTER(i32), c.c_char_p]
     lib.smapb_plan_info.argtypes = [vp, i32, c.POINTER(i32), c.POINTER(c.c_double)]
-    lib.smapb_conv_test.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp,
+    lib.smapb_conv_test.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp,
                                     c.POINTER(c.c_float), vp]
     for name in EXPORTS:
         fn = getattr(lib, name)

@@ -718,7 +718,10 @@ lift_kernel(const float* __restrict__ bodies, const int* __restrict__ counts, co
         pred3d[i] = 0.0;
     }
     for (int i = NP + tid; i < MAXP; i += LIFT_THREADS) root_depth[i] = 0.0;
-    if (tid == 0) counts_out[(size_t)img * scnt] = NP;
+    if (tid == 0) {
+        counts_out[(size_t)img * scnt] = NP;
+        if (scnt > 1) counts_out[(size_t)img * scnt + 1] = 0;  // smapb_record::pad_
+    }
     pdl_trigger();
 }
 

@@ -13,10 +13,15 @@
 // (dropped terms are O(2^-16) relative) - fp32-faithful results at 3x the bf16 MMA count.  NTERMS = 1 is the
 // plain bf16 fast mode.
 //
-// Warp roles (256 threads, persistent CTA, static tile schedule):
-//   warp 0 : TMA producer (one elected lane)        warp 1 : MMA issuer (one elected lane)
-//   warp 2 : TMEM allocator                         warps 4-7 : epilogue (TMEM -> regs -> global)
-// Pipelines: smem full/empty ring (TMA <-> MMA), double-buffered TMEM accumulators (MMA <-> epilogue).
+// Warp roles (384 threads, persistent CTA, static tile schedule):
+//   warp 0 : operand TMA producer (one lane)        warp 1 : MMA issuer (one lane)
+//   warp 2 : TMEM allocator                         warp 3 : residual TMA producer (one lane)
+//   warps 4-11 : epilogue, two groups of 4 warps taking alternate 32-column chunks:
+//                TMEM -> regs (+bias +residual, ReLU, hi/lo split) -> swizzled smem -> TMA store
+// Pipelines: operand full/empty ring (TMA <-> MMA), double-buffered TMEM accumulators (MMA <-> epilogue),
+// residual full/empty ring (TMA <-> epilogue), bulk-async store groups (epilogue <-> TMA store).
+// The epilogue never touches global memory with per-thread loads/stores on the main path: the residual tile
+// arrives by TMA ahead of time and the output leaves by TMA in 32-channel x 128-pixel boxes.
 #pragma once
 #include <cuda.h>
 #include "common.cuh"
@@ -24,8 +29,10 @@
 namespace smapb {
 
 struct alignas(64) ConvParams {
-    CUtensorMap tmA;
-    CUtensorMap tmB;
+    CUtensorMap tmA;  // activations (loads)
+    CUtensorMap tmB;  // weights (loads)
+    CUtensorMap tmO;  // output planes (stores, 32-channel boxes, SWIZZLE_64B)
+    CUtensorMap tmR[3];  // epilogue input planes (loads, same geometry as tmO): [residual][post1][post2] as present
     // geometry
     int Hout, Wout, Nimg;
     int tw_log2, th;  // tile: tw = 1 << tw_log2, tw * th == 128
@@ -37,13 +44,13 @@ struct alignas(64) ConvParams {
     int total_tiles;
     // epilogue
     const float* bias;           // [Cout_pad] folded bias
-    const __nv_bfloat16* res;    // residual added before ReLU (hi plane; lo plane at + plane_stride) or null
-    const __nv_bfloat16* post1;  // added after ReLU (x_k = layer_k + skip1 + skip2, model/smap.py:143) or null
-    const __nv_bfloat16* post2;
+    int has_res;  // tmR[0] is a residual added before the ReLU (model/smap.py:74-75)
+    int n_post;   // number of tensors added after the ReLU (x_k = layer_k + skip1 + skip2, model/smap.py:143)
     __nv_bfloat16* out;  // bf16 hi/lo planes NHWC, or null
     float* out_f32;      // fp32 NHWC (heads), or null
     long long plane_stride;  // elements between the hi and lo planes (= N*H*W*Cout)
     int relu;
+    int one_group;  // debug: epilogue group 0 takes every chunk
 };
 
 // ---- tcgen05 / TMA PTX wrappers -----------------------------------------------------------------
@@ -109,16 +116,56 @@ __device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
     return r;
 }
 
+
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3,
+                                             int c4) {
+    asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(map),
+                 "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ uint4 lds_v4(uint32_t addr) {
+    uint4 r;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
+    return r;
+}
+__device__ __forceinline__ void sts_v4(uint32_t addr, uint4 v) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+                 : "memory");
+}
+// byte offset of 16-byte chunk j (0..3) of row r in a [128 rows x 64 B] SWIZZLE_64B box
+__device__ __forceinline__ uint32_t sw64_off(int r, int j) { return (uint32_t)(r * 64 + ((j ^ ((r >> 1) & 3)) << 4)); }
+
+__device__ __forceinline__ uint4 ldg_v4(const void* p) {
+    uint4 r;
+    asm volatile("ld.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+    return r;
+}
+
 template <int BLOCK_N, int NTERMS>
 struct ConvCfg {
     static constexpr int TA = (NTERMS == 3) ? 2 : 1;  // operand planes held per stage
     static constexpr int A_BYTES = 128 * 128;         // 128 rows x 64 bf16
     static constexpr int B_BYTES = BLOCK_N * 128;
     static constexpr int STAGE_BYTES = TA * (A_BYTES + B_BYTES);
-    static constexpr int SMEM_BUDGET = 227 * 1024 - 2048;
-    static constexpr int STAGES_RAW = SMEM_BUDGET / STAGE_BYTES;
+    static constexpr int CHUNK_COLS = 32;              // epilogue granularity (one tcgen05.ld x32)
+    static constexpr int CHUNKS = BLOCK_N / CHUNK_COLS;
+    static constexpr int CHUNK_BYTES = 128 * 64;       // one plane of one chunk: 128 rows x 32 bf16
+    static constexpr int SLOT_BYTES = TA * CHUNK_BYTES;  // hi (+ lo)
+    static constexpr int OUT_BUFS = 2;  // one staging slot per epilogue group
+    static constexpr int RES_BUFS = (BLOCK_N >= 128) ? 4 : 2;
+    static constexpr int SPG = RES_BUFS / 2;  // ring slots per epilogue group
+    static constexpr int EPI_BYTES = (OUT_BUFS + RES_BUFS) * SLOT_BYTES;
+    static constexpr int SMEM_LIMIT = 227 * 1024;
+    static constexpr int STAGES_RAW = (SMEM_LIMIT - 2048 - EPI_BYTES) / STAGE_BYTES;
     static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2048;  // 1 KB barriers + 1 KB alignment slack
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 2048;  // 1 KB control + 1 KB alignment slack
     static constexpr int TMEM_COLS = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64) ? 64 : (2 * BLOCK_N <= 128) ? 128
                                      : (2 * BLOCK_N <= 256) ? 256 : 512;
     static_assert(STAGES >= 2, "need at least a double buffer");
@@ -126,24 +173,32 @@ struct ConvCfg {
 };
 
 template <int BLOCK_N, int NTERMS>
-__global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__ ConvParams p) {
+__global__ void __launch_bounds__(384, 1) conv_tc_kernel(const __grid_constant__ ConvParams p) {
     using Cfg = ConvCfg<BLOCK_N, NTERMS>;
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ unsigned char smem_raw[];
-    // control block at the front, operand ring 1024-aligned behind it
+    // control block at the front, operand ring + epilogue staging 1024-aligned behind it
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw);
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tfull_bar = empty_bar + STAGES;
     uint64_t* tempty_bar = tfull_bar + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    uint64_t* rfull_bar = tempty_bar + 2;
+    uint64_t* rempty_bar = rfull_bar + Cfg::RES_BUFS;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rempty_bar + Cfg::RES_BUFS);
     const uint32_t ring = (smem_u32(smem_raw) + 1024u + 1023u) & ~1023u;
+    const uint32_t out_stage = ring + STAGES * Cfg::STAGE_BYTES;
+    const uint32_t res_stage = out_stage + Cfg::OUT_BUFS * Cfg::SLOT_BYTES;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    const int n_extra = p.has_res + p.n_post;  // epilogue input tensors streamed through the residual ring
+    const bool tma_out = p.out != nullptr;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&p.tmA);
         tma_prefetch_desc(&p.tmB);
+        if (tma_out) tma_prefetch_desc(&p.tmO);
+        for (int e = 0; e < n_extra; e++) tma_prefetch_desc(&p.tmR[e]);
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; s++) {
@@ -152,7 +207,11 @@ __global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__
         }
         for (int a = 0; a < 2; a++) {
             mbar_init(&tfull_bar[a], 1);
-            mbar_init(&tempty_bar[a], 128);
+            mbar_init(&tempty_bar[a], 256);
+        }
+        for (int s = 0; s < Cfg::RES_BUFS; s++) {
+            mbar_init(&rfull_bar[s], 1);
+            mbar_init(&rempty_bar[s], 128);
         }
         fence_mbar_init();
     }
@@ -174,7 +233,7 @@ __global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__
     pdl_wait();  // inputs of this layer are produced by the previous kernel in the stream
 
     if (warp == 0) {
-        // ============================ TMA producer ============================
+        // ============================ operand TMA producer ====================
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
@@ -247,12 +306,43 @@ __global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__
                 }
             }
         }
+    } else if (warp == 3) {
+        // ============================ residual TMA producer ===================
+        if (lane == 0 && n_extra > 0) {
+            // Each epilogue group owns its own slice of the ring (slots [g*SPG, (g+1)*SPG)), so every slot is
+            // always consumed by the same 128 threads in FIFO order - a waiter can never be more than one
+            // mbarrier phase ahead of the fill it is waiting for.
+            int cnt[2] = {0, 0};  // fills issued so far per group
+            const int one = p.one_group;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
+                const int img = mt / tiles_per_img, r = mt - img * tiles_per_img;
+                const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
+                for (int c = 0; c < Cfg::CHUNKS; c++) {
+                    const int g = one ? 0 : (c & 1);
+                    for (int e = 0; e < n_extra; e++) {
+                        const int m = cnt[g]++;
+                        const int slot = g * Cfg::SPG + (m % Cfg::SPG);
+                        mbar_wait(&rempty_bar[slot], ((uint32_t)(m / Cfg::SPG) & 1u) ^ 1u);
+                        mbar_arrive_expect_tx(&rfull_bar[slot], Cfg::SLOT_BYTES);
+#pragma unroll
+                        for (int t = 0; t < Cfg::TA; t++)
+                            tma_load_5d(res_stage + slot * Cfg::SLOT_BYTES + t * Cfg::CHUNK_BYTES, &p.tmR[e],
+                                        &rfull_bar[slot], nt * BLOCK_N + c * 32, tx << p.tw_log2, ty * p.th, img, t);
+                    }
+                }
+            }
+        }
     } else if (warp >= 4) {
         // ============================ epilogue ================================
-        const int q = warp & 3;  // TMEM lane quarter this warp may access
+        const int q = warp & 3;          // TMEM lane quarter this warp may access
+        const int g = (warp - 4) >> 2;   // epilogue group: chunks c = g, g+2, ...
         const int row = q * 32 + lane;
+        const bool leader = (threadIdx.x == 128 + g * 128);
+        const uint32_t ob = out_stage + g * Cfg::SLOT_BYTES;
         int acc = 0;
         uint32_t acc_phase = 0;
+        int rcnt = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
             const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
             const int img = mt / tiles_per_img, r = mt - img * tiles_per_img;
@@ -267,20 +357,37 @@ __global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__
             tc_fence_after();
             const uint32_t taddr = tmem_base + (uint32_t)(acc * BLOCK_N) + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
-            for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+            for (int c = (p.one_group ? (g == 0 ? 0 : Cfg::CHUNKS) : g); c < Cfg::CHUNKS; c += (p.one_group ? 1 : 2)) {
+                const int c0 = c * 32;
                 uint32_t acc_r[32];
                 tmem_ld32(taddr + (uint32_t)c0, acc_r);
-                // residual operands for this chunk are fetched while the TMEM load is in flight
-                const long long off = pix * p.Cout + n0 + c0;
-                uint4 rh[4], rl[4];
-                const bool has_res = valid && (p.res != nullptr);
-                if (has_res) {
+                // epilogue inputs arrive through the residual ring in the order [residual][post1][post2]
+                auto ring_fetch = [&](uint4(&hh)[4], uint4(&ll)[4]) {
+                    const int m = rcnt++;  // this group's FIFO position (mirrors the producer's cnt[g])
+                    const int rslot = g * Cfg::SPG + (m % Cfg::SPG);
+                    mbar_wait(&rfull_bar[rslot], (uint32_t)(m / Cfg::SPG) & 1u);
+                    const uint32_t rb = res_stage + rslot * Cfg::SLOT_BYTES;
 #pragma unroll
                     for (int j = 0; j < 4; j++) {
-                        rh[j] = ldg_nc_v4(p.res + off + j * 8);
-                        rl[j] = (NTERMS == 3) ? ldg_nc_v4(p.res + p.plane_stride + off + j * 8) : make_uint4(0, 0, 0, 0);
+                        hh[j] = lds_v4(rb + sw64_off(row, j));
+                        ll[j] = (NTERMS == 3) ? lds_v4(rb + Cfg::CHUNK_BYTES + sw64_off(row, j)) : make_uint4(0, 0, 0, 0);
                     }
-                }
+                    mbar_arrive(&rempty_bar[rslot]);  // values are in registers: the slot can be refilled
+                };
+                auto add_planes = [&](float(&vv)[32], const uint4(&hh)[4], const uint4(&ll)[4]) {
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const uint32_t h[4] = {hh[j].x, hh[j].y, hh[j].z, hh[j].w};
+                        const uint32_t l[4] = {ll[j].x, ll[j].y, ll[j].z, ll[j].w};
+#pragma unroll
+                        for (int e = 0; e < 4; e++) {
+                            vv[8 * j + 2 * e] += bf16lo_to_f(h[e]) + bf16lo_to_f(l[e]);
+                            vv[8 * j + 2 * e + 1] += bf16hi_to_f(h[e]) + bf16hi_to_f(l[e]);
+                        }
+                    }
+                };
+                uint4 rh[4], rl[4];
+                if (p.has_res) ring_fetch(rh, rl);
                 tmem_ld_wait();
                 float v[32];
 #pragma unroll
@@ -291,67 +398,49 @@ __global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__
                     v[4 * j + 2] = __uint_as_float(acc_r[4 * j + 2]) + b.z;
                     v[4 * j + 3] = __uint_as_float(acc_r[4 * j + 3]) + b.w;
                 }
-                if (has_res) {
-#pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        const uint32_t h[4] = {rh[j].x, rh[j].y, rh[j].z, rh[j].w};
-                        const uint32_t l[4] = {rl[j].x, rl[j].y, rl[j].z, rl[j].w};
-#pragma unroll
-                        for (int e = 0; e < 4; e++) {
-                            v[8 * j + 2 * e] += bf16lo_to_f(h[e]) + bf16lo_to_f(l[e]);
-                            v[8 * j + 2 * e + 1] += bf16hi_to_f(h[e]) + bf16hi_to_f(l[e]);
-                        }
-                    }
-                }
+                if (p.has_res) add_planes(v, rh, rl);
                 if (p.relu) {
 #pragma unroll
                     for (int j = 0; j < 32; j++) v[j] = fmaxf(v[j], 0.f);
                 }
-                if (valid && p.post1 != nullptr) {
-#pragma unroll
-                    for (int s = 0; s < 2; s++) {
-                        const __nv_bfloat16* src = s == 0 ? p.post1 : p.post2;
-                        if (src == nullptr) continue;
-#pragma unroll
-                        for (int j = 0; j < 4; j++) {
-                            const uint4 hh = ldg_nc_v4(src + off + j * 8);
-                            const uint4 ll =
-                                (NTERMS == 3) ? ldg_nc_v4(src + p.plane_stride + off + j * 8) : make_uint4(0, 0, 0, 0);
-                            const uint32_t h[4] = {hh.x, hh.y, hh.z, hh.w};
-                            const uint32_t l[4] = {ll.x, ll.y, ll.z, ll.w};
-#pragma unroll
-                            for (int e = 0; e < 4; e++) {
-                                v[8 * j + 2 * e] += bf16lo_to_f(h[e]) + bf16lo_to_f(l[e]);
-                                v[8 * j + 2 * e + 1] += bf16hi_to_f(h[e]) + bf16hi_to_f(l[e]);
-                            }
-                        }
-                    }
+                for (int e = 0; e < p.n_post; e++) {  // (relu(..) + skip1) + skip2, left to right
+                    ring_fetch(rh, rl);
+                    add_planes(v, rh, rl);
                 }
-                if (valid) {
-                    if (p.out != nullptr) {
+                const long long off = pix * p.Cout + n0 + c0;
+                if (tma_out) {
+                    // this group's staging slot must have been drained by its previous TMA store
+                    if (leader) bulk_wait_read<0>();
+                    epi_bar_sync(1 + g);
 #pragma unroll
-                        for (int j = 0; j < 4; j++) {
-                            uint32_t hw_[4], lw_[4];
+                    for (int j = 0; j < 4; j++) {
+                        uint32_t hw_[4], lw_[4];
 #pragma unroll
-                            for (int e = 0; e < 4; e++) {
-                                __nv_bfloat16 h0, l0, h1, l1;
-                                split_bf16(v[8 * j + 2 * e], h0, l0);
-                                split_bf16(v[8 * j + 2 * e + 1], h1, l1);
-                                hw_[e] = pack_bf16x2(h0, h1);
-                                lw_[e] = pack_bf16x2(l0, l1);
-                            }
-                            *reinterpret_cast<uint4*>(p.out + off + j * 8) = make_uint4(hw_[0], hw_[1], hw_[2], hw_[3]);
-                            if (NTERMS == 3)
-                                *reinterpret_cast<uint4*>(p.out + p.plane_stride + off + j * 8) =
-                                    make_uint4(lw_[0], lw_[1], lw_[2], lw_[3]);
+                        for (int e = 0; e < 4; e++) {
+                            const float a = v[8 * j + 2 * e], b = v[8 * j + 2 * e + 1];
+                            const __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);  // one cvt.rn.bf16x2.f32
+                            const uint32_t hw = *reinterpret_cast<const uint32_t*>(&h2);
+                            const __nv_bfloat162 l2 = __floats2bfloat162_rn(a - bf16lo_to_f(hw), b - bf16hi_to_f(hw));
+                            hw_[e] = hw;
+                            lw_[e] = *reinterpret_cast<const uint32_t*>(&l2);
                         }
+                        sts_v4(ob + sw64_off(row, j), make_uint4(hw_[0], hw_[1], hw_[2], hw_[3]));
+                        if (NTERMS == 3)
+                            sts_v4(ob + Cfg::CHUNK_BYTES + sw64_off(row, j), make_uint4(lw_[0], lw_[1], lw_[2], lw_[3]));
                     }
-                    if (p.out_f32 != nullptr) {
+                    fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA store
+                    epi_bar_sync(1 + g);
+                    if (leader) {
 #pragma unroll
-                        for (int j = 0; j < 8; j++)
-                            *reinterpret_cast<float4*>(p.out_f32 + off + j * 4) =
-                                make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                        for (int t = 0; t < Cfg::TA; t++)
+                            tma_store_5d(&p.tmO, ob + t * Cfg::CHUNK_BYTES, n0 + c0, tx << p.tw_log2, ty * p.th, img, t);
+                        bulk_commit();
                     }
+                } else if (valid) {  // fp32 NHWC heads: small tensors, direct stores
+#pragma unroll
+                    for (int j = 0; j < 8; j++)
+                        *reinterpret_cast<float4*>(p.out_f32 + off + j * 4) =
+                            make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                 }
             }
             tc_fence_before();
@@ -361,6 +450,7 @@ __global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__
                 acc_phase ^= 1u;
             }
         }
+        if (leader && tma_out) bulk_wait_all();  // stores must be complete before the CTA retires
     }
 
     pdl_trigger();

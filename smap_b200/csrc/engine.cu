@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -179,17 +180,18 @@ int dev_alloc(smapb_handle* h, T** p, size_t count) {
 // tensor maps
 // ------------------------------------------------------------------------------------------------
 int make_act_map(smapb_handle* h, CUtensorMap* m, const __nv_bfloat16* ptr, long long C, long long W, long long H,
-                 long long N, int T, long long plane_elems, int box_w, int box_h, int stride) {
+                 long long N, int T, long long plane_elems, int box_w, int box_h, int stride, int box_c = 64) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) return fail(h, -20, "cuTensorMapEncodeTiled entry point not available");
     cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N, (cuuint64_t)T};
     cuuint64_t strides[4] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2,
                              (cuuint64_t)plane_elems * 2};
-    cuuint32_t box[5] = {64, (cuuint32_t)box_w, (cuuint32_t)box_h, 1, 1};
+    cuuint32_t box[5] = {(cuuint32_t)box_c, (cuuint32_t)box_w, (cuuint32_t)box_h, 1, 1};
     cuuint32_t es[5] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1, 1};
+    // 64-channel boxes (operands) use 128-byte rows, 32-channel boxes (epilogue tiles) 64-byte rows
     CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, (void*)ptr, dims, strides, box, es,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, box_c == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         char buf[256];
         snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled(act) failed: %d  dims=(%lld,%lld,%lld,%lld,%d) box=(64,%d,%d) s=%d",
@@ -228,7 +230,7 @@ cudaError_t launch_conv_inst(const ConvParams& cp, int grid, cudaStream_t st, bo
     }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(256);
+    cfg.blockDim = dim3(384);
     cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -244,7 +246,8 @@ cudaError_t launch_conv(const ConvParams& cp, int block_n, int nterms, int sm_co
     case BN:                                                                        \
         return nterms == 3 ? launch_conv_inst<BN, 3>(cp, grid, st, pdl) : launch_conv_inst<BN, 1>(cp, grid, st, pdl);
     switch (block_n) {
-        SMAPB_CASE(256)
+        case 256:  // only the single-term mode has room for 256-wide operand stages next to the epilogue staging
+            return nterms == 1 ? launch_conv_inst<256, 1>(cp, grid, st, pdl) : cudaErrorInvalidValue;
         SMAPB_CASE(128)
         SMAPB_CASE(64)
         SMAPB_CASE(32)
@@ -308,8 +311,12 @@ int setup_conv(smapb_handle* h, const ConvLayer& L, const Act& in, const Act* re
     // BLOCK_N: the largest tile that still yields at least one full wave of CTAs, else the smallest >= 64
     int bn = 0;
     const int cands[4] = {256, 128, 64, 32};
+    // 256-wide tiles leave room for only single-buffered epilogue staging: keep them for long-K layers without
+    // a residual stream (compute-bound), use <= 128 elsewhere
+    const bool allow256 = (h->nterms == 1) && (res == nullptr) && (L.Cin * L.k * L.k >= 512);
     for (int c : cands) {
         if (L.Cout_pad % c) continue;
+        if (c == 256 && !allow256) continue;
         if (m_tiles * (L.Cout_pad / c) >= h->sm_count) {
             bn = c;
             break;
@@ -330,15 +337,37 @@ int setup_conv(smapb_handle* h, const ConvLayer& L, const Act& in, const Act* re
     cp->n_tiles = L.Cout_pad / bn;
     cp->total_tiles = (int)(m_tiles * cp->n_tiles);
     cp->bias = L.bias_dev;
-    cp->res = res ? res->ptr : nullptr;
-    cp->post1 = post1 ? post1->ptr : nullptr;
-    cp->post2 = post2 ? post2->ptr : nullptr;
+    cp->has_res = res ? 1 : 0;
+    cp->n_post = (post1 ? 1 : 0) + (post2 ? 1 : 0);
+    if (post2 && !post1) return fail(h, -30, "conv " + L.name + ": post2 without post1");
     cp->out = out ? out->ptr : nullptr;
     cp->out_f32 = outf ? outf->ptr : nullptr;
     cp->plane_stride = (long long)N * Ho * Wo * L.Cout_pad;
     cp->relu = relu;
+    {
+        const char* og = getenv("SMAPB_DEBUG_ONEGROUP");  // debug: any of 'f' (fp32-out), 'p' (post adds), 'r' (residual), 'o' (others)
+        cp->one_group = 0;
+        if (og) {
+            const bool is_f = outf != nullptr, is_p = post1 != nullptr, is_r = res != nullptr && !is_p;
+            if ((is_f && strchr(og, 'f')) || (is_p && strchr(og, 'p')) || (is_r && strchr(og, 'r')) ||
+                (!is_f && !is_p && !is_r && strchr(og, 'o')))
+                cp->one_group = 1;
+        }
+    }
     rc = make_w_map(h, &cp->tmB, L.w_dev, L.Cin, L.Cout_pad, L.k * L.k, h->planes, bn);
     if (rc) return rc;
+    // epilogue tiles: 32 channels x (tw x th) pixels of the output / residual planes
+    int n_in = 0;
+    for (int which = 0; which < 4; which++) {
+        const Act* t = which == 0 ? out : which == 1 ? res : which == 2 ? post1 : post2;
+        if (!t) continue;
+        CUtensorMap* m = which == 0 ? &cp->tmO : &cp->tmR[n_in++];
+        if (flat)
+            rc = make_act_map(h, m, t->ptr, L.Cout_pad, (long long)N * Ho * Wo, 1, 1, h->planes, t->plane(), 128, 1, 1, 32);
+        else
+            rc = make_act_map(h, m, t->ptr, L.Cout_pad, Wo, Ho, N, h->planes, t->plane(), tw, th, 1, 32);
+        if (rc) return rc;
+    }
     *block_n_out = bn;
     if (flops_out) *flops_out = 2.0 * N * Ho * Wo * (double)L.Cout * L.Cin * L.k * L.k;
     return 0;
@@ -636,6 +665,7 @@ int run_plan(smapb_handle* h, Plan* plan, const float* imgs, float* hm2d, float*
             }
         }
         h->launches++;
+        if (getenv("SMAPB_DEBUG_SYNC")) CK(cudaStreamSynchronize(st));
     }
     return 0;
 }
@@ -1018,9 +1048,9 @@ __global__ void split_to_f32_kernel(const __nv_bfloat16* __restrict__ in, long l
     out[i] = v;
 }
 
-int smapb_conv_test(smapb_handle* h, const float* x, const float* w, const float* bias, const float* res, int B,
-                    int H, int W, int Cin, int Cout, int k, int stride, int relu, int precision, float* y,
-                    float* ms_out, void* stream) {
+int smapb_conv_test(smapb_handle* h, const float* x, const float* w, const float* bias, const float* res,
+                    const float* post1, const float* post2, int B, int H, int W, int Cin, int Cout, int k, int stride,
+                    int relu, int precision, float* y, float* ms_out, void* stream) {
     if (!h) return -1;
     cudaSetDevice(h->device);
     cudaStream_t st = (cudaStream_t)stream;
@@ -1056,10 +1086,12 @@ int smapb_conv_test(smapb_handle* h, const float* x, const float* w, const float
         return rc;
     }
     const int Ho = (H + 2 * L.pad - k) / stride + 1, Wo = (W + 2 * L.pad - k) / stride + 1;
-    Act in, out, r;
+    Act in, out, r, p1, p2;
     in.N = B, in.H = H, in.W = W, in.C = Cin;
     out.N = B, out.H = Ho, out.W = Wo, out.C = L.Cout_pad;
     r = out;
+    p1 = out;
+    p2 = out;
     void* p = nullptr;
     CKT(cudaMalloc(&p, (size_t)in.plane() * 2 * h->planes));
     tmp.push_back(p);
@@ -1068,19 +1100,23 @@ int smapb_conv_test(smapb_handle* h, const float* x, const float* w, const float
     tmp.push_back(p);
     out.ptr = (__nv_bfloat16*)p;
     CKT(launch_f32_to_split(x, in.ptr, in.plane(), in.plane(), h->planes, st));
-    if (res) {
+    const float* extra_src[3] = {res, post1, post2};
+    Act* extra_act[3] = {&r, &p1, &p2};
+    for (int e = 0; e < 3; e++) {
+        if (!extra_src[e]) continue;
         if (L.Cout_pad != Cout) {
             cleanup();
-            return fail(h, -1, "conv_test: residual requires Cout % 32 == 0");
+            return fail(h, -1, "conv_test: residual/post operands require Cout % 32 == 0");
         }
         CKT(cudaMalloc(&p, (size_t)out.plane() * 2 * h->planes));
         tmp.push_back(p);
-        r.ptr = (__nv_bfloat16*)p;
-        CKT(launch_f32_to_split(res, r.ptr, r.plane(), r.plane(), h->planes, st));
+        extra_act[e]->ptr = (__nv_bfloat16*)p;
+        CKT(launch_f32_to_split(extra_src[e], extra_act[e]->ptr, out.plane(), out.plane(), h->planes, st));
     }
     ConvParams cp;
     int bn = 0;
-    rc = setup_conv(h, L, in, res ? &r : nullptr, nullptr, nullptr, &out, nullptr, relu, &cp, &bn, nullptr);
+    rc = setup_conv(h, L, in, res ? &r : nullptr, post1 ? &p1 : nullptr, post2 ? &p2 : nullptr, &out, nullptr, relu,
+                    &cp, &bn, nullptr);
     if (rc) {
         cleanup();
         return rc;

@@ -171,7 +171,8 @@ class Engine:
         self._check(self.lib.smapb_plan_info(self._h, B, ctypes.byref(n), ctypes.byref(f)), "smapb_plan_info")
         return n.value, f.value
 
-    def conv_test(self, x, w, bias, res=None, stride=1, relu=True, precision="bf16x3", time_it=False):
+    def conv_test(self, x, w, bias, res=None, stride=1, relu=True, precision="bf16x3", time_it=False, post1=None,
+                  post2=None):
         """x fp32 NHWC cuda; w [Cout,Cin,k,k]; returns y fp32 NHWC (and ms)."""
         B, H, W, Cin = x.shape
         Cout, _, k, _ = w.shape
@@ -180,7 +181,9 @@ class Engine:
         y = torch.empty(B, Ho, Wo, Cout, device=x.device)
         ms = ctypes.c_float(0)
         self._check(self.lib.smapb_conv_test(self._h, _ptr(x.contiguous()), _ptr(w.contiguous()), _ptr(bias.contiguous()),
-                                             _ptr(res.contiguous() if res is not None else None), B, H, W, Cin, Cout, k,
+                                             _ptr(res.contiguous() if res is not None else None),
+                                             _ptr(post1.contiguous() if post1 is not None else None),
+                                             _ptr(post2.contiguous() if post2 is not None else None), B, H, W, Cin, Cout, k,
                                              stride, int(relu), PRECISIONS[precision], _ptr(y),
                                              ctypes.byref(ms) if time_it else None, _stream()), "smapb_conv_test")
         return (y, ms.value) if time_it else y

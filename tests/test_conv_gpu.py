@@ -31,6 +31,12 @@ CASES = [
     (1, 32, 52, 256, 14, 3, 1, False, False),    # thin head, Cout padded to 32
     (1, 16, 24, 256, 1, 3, 1, False, False),     # root-depth head
     (2, 16, 26, 2048, 512, 1, 1, True, False),   # long K (32 k-blocks): ring wrap-around
+    # persistent regime: many tiles per CTA (accumulator / residual / staging rings wrap many times)
+    (8, 128, 208, 64, 256, 1, 1, True, True),    # layer1 conv3 + residual, 3328 tiles
+    (8, 128, 208, 256, 64, 1, 1, True, False),   # N=64 tiles, 2 chunks
+    (4, 128, 208, 64, 64, 3, 1, True, False),    # 3x3 patch tiles, 832 tiles
+    (8, 64, 104, 128, 512, 1, 1, False, True),   # layer2 conv3 + residual
+    (8, 128, 208, 256, 14, 3, 1, False, False),  # N=32 single-chunk tiles (one epilogue group idle)
 ]
 
 
@@ -65,3 +71,19 @@ def test_conv_bf16_fast_mode_is_coarser_but_sane(eng):
     y = eng.conv_test(x, w, b, relu=False, precision="bf16")
     err = (y - ref).abs().max().item() / ref.abs().max().item()
     assert err < 2e-2
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(2, 128, 208, 64, 256), (8, 64, 104, 128, 512), (1, 16, 26, 512, 2048)])
+def test_conv_residual_and_post_adds_deterministic(eng, B, H, W, Cin, Cout):
+    """Last bottleneck of a layer in stages 1-2: relu(conv3 + x) + skip1 + skip2 (model/smap.py:74-75,143)."""
+    g = torch.Generator(device="cpu").manual_seed(7)
+    x = torch.randn(B, H, W, Cin, generator=g).cuda()
+    w = (torch.randn(Cout, Cin, 1, 1, generator=g) / Cin ** 0.5).cuda()
+    b = torch.randn(Cout, generator=g).cuda()
+    res, p1, p2 = (torch.randn(B, H, W, Cout, generator=g).cuda() for _ in range(3))
+    ref = F.relu(F.conv2d(x.permute(0, 3, 1, 2), w, b).permute(0, 2, 3, 1) + res) + p1 + p2
+    ys = [eng.conv_test(x, w, b, res=res, relu=True, post1=p1, post2=p2) for _ in range(4)]
+    torch.cuda.synchronize()
+    for y in ys:
+        assert torch.equal(y, ys[0]), "non-deterministic output"
+        assert (y - ref).abs().max().item() / ref.abs().max().item() < 2e-5
