@@ -150,6 +150,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
 
+    from smap_b200 import dist as sdist
     from smap_b200 import schema
     from smap_b200.engine import RECORD_BYTES, Engine, scale_row
 
@@ -172,19 +173,16 @@ def run_ours(args):
               f_y=1920.0, cx=960.0, cy=540.0)
     scales_host = torch.from_numpy(np.stack([scale_row(sc)] * B)).pin_memory()
     scales_dev = scales_host.to(dev)
-    gathered = torch.empty(world * B, RECORD_BYTES, dtype=torch.uint8, device=dev) if world > 1 else None
     host_out = torch.empty(B, RECORD_BYTES, dtype=torch.uint8).pin_memory()
 
     def step_device(i):
         rec = eng.infer_device(dev_batches[i % NROT], scales_dev, do_flip=bool(args.flip))
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, rec)
-        return rec
+        return sdist.allgather_records(rec)  # one NCCL all-gather of the skeleton records (no-op at world 1)
 
     def step_host(i):
         recs = eng.infer_host(host_batches[i % NROT], scales_host, do_flip=bool(args.flip), out=host_out)
         if world > 1:
-            dist.all_gather_into_tensor(gathered, torch.from_numpy(host_out.numpy()).to(dev, non_blocking=True))
+            sdist.allgather_records(host_out.to(dev, non_blocking=True))
             torch.cuda.synchronize()
         return recs
 
