@@ -148,7 +148,7 @@ __device__ __forceinline__ uint4 ldg_v4(const void* p) {
     return r;
 }
 
-template <int BLOCK_N, int NTERMS>
+template <int BLOCK_N, int NTERMS, bool RING>
 struct ConvCfg {
     static constexpr int TA = (NTERMS == 3) ? 2 : 1;  // operand planes held per stage
     static constexpr int A_BYTES = 128 * 128;         // 128 rows x 64 bf16
@@ -159,8 +159,9 @@ struct ConvCfg {
     static constexpr int CHUNK_BYTES = 128 * 64;       // one plane of one chunk: 128 rows x 32 bf16
     static constexpr int SLOT_BYTES = TA * CHUNK_BYTES;  // hi (+ lo)
     static constexpr int OUT_BUFS = 2;  // one staging slot per epilogue group
-    static constexpr int RES_BUFS = (BLOCK_N >= 128) ? 4 : 2;
-    static constexpr int SPG = RES_BUFS / 2;  // ring slots per epilogue group
+    // RING: the layer streams epilogue inputs (residual / skip adds); without it the smem goes to operand stages
+    static constexpr int RES_BUFS = !RING ? 0 : (BLOCK_N >= 128) ? 4 : 2;
+    static constexpr int SPG = RING ? RES_BUFS / 2 : 1;  // ring slots per epilogue group
     static constexpr int EPI_BYTES = (OUT_BUFS + RES_BUFS) * SLOT_BYTES;
     static constexpr int SMEM_LIMIT = 227 * 1024;
     static constexpr int STAGES_RAW = (SMEM_LIMIT - 2048 - EPI_BYTES) / STAGE_BYTES;
@@ -172,9 +173,9 @@ struct ConvCfg {
     static_assert(BLOCK_N % 32 == 0 && BLOCK_N >= 32 && BLOCK_N <= 256, "BLOCK_N");
 };
 
-template <int BLOCK_N, int NTERMS>
+template <int BLOCK_N, int NTERMS, bool RING>
 __global__ void __launch_bounds__(384, 1) conv_tc_kernel(const __grid_constant__ ConvParams p) {
-    using Cfg = ConvCfg<BLOCK_N, NTERMS>;
+    using Cfg = ConvCfg<BLOCK_N, NTERMS, RING>;
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ unsigned char smem_raw[];
     // control block at the front, operand ring + epilogue staging 1024-aligned behind it
@@ -191,7 +192,7 @@ __global__ void __launch_bounds__(384, 1) conv_tc_kernel(const __grid_constant__
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int n_extra = p.has_res + p.n_post;  // epilogue input tensors streamed through the residual ring
+    const int n_extra = RING ? p.has_res + p.n_post : 0;  // epilogue input tensors streamed through the ring
     const bool tma_out = p.out != nullptr;
 
     if (warp == 0 && lane == 0) {
@@ -387,7 +388,7 @@ __global__ void __launch_bounds__(384, 1) conv_tc_kernel(const __grid_constant__
                     }
                 };
                 uint4 rh[4], rl[4];
-                if (p.has_res) ring_fetch(rh, rl);
+                if (RING && p.has_res) ring_fetch(rh, rl);
                 tmem_ld_wait();
                 float v[32];
 #pragma unroll
@@ -398,12 +399,12 @@ __global__ void __launch_bounds__(384, 1) conv_tc_kernel(const __grid_constant__
                     v[4 * j + 2] = __uint_as_float(acc_r[4 * j + 2]) + b.z;
                     v[4 * j + 3] = __uint_as_float(acc_r[4 * j + 3]) + b.w;
                 }
-                if (p.has_res) add_planes(v, rh, rl);
+                if (RING && p.has_res) add_planes(v, rh, rl);
                 if (p.relu) {
 #pragma unroll
                     for (int j = 0; j < 32; j++) v[j] = fmaxf(v[j], 0.f);
                 }
-                for (int e = 0; e < p.n_post; e++) {  // (relu(..) + skip1) + skip2, left to right
+                for (int e = 0; RING && e < p.n_post; e++) {  // (relu(..) + skip1) + skip2, left to right
                     ring_fetch(rh, rl);
                     add_planes(v, rh, rl);
                 }

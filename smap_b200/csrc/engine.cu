@@ -129,7 +129,15 @@ struct smapb_handle {
     float* scratch_rootd = nullptr;
     double* scales_dev = nullptr;
     smapb_record* records_dev = nullptr;
-    bool use_graph = true;
+    cudaStream_t own_stream = nullptr;  // blocking stream used when the caller passes the legacy default stream
+    struct GraphEntry {
+        int B, flip;
+        const void* imgs;
+        const void* scales;
+        cudaGraphExec_t exec;
+    };
+    std::vector<GraphEntry> graphs;  // whole-path CUDA graphs keyed by (B, flip, input pointers)
+    std::map<std::pair<int, int>, int> eager_runs;  // (B, flip) -> number of eager executions so far
     // profiling (per-op CUDA events on the launching stream)
     bool profiling = false;
     std::vector<cudaEvent_t> prof_events;
@@ -218,13 +226,13 @@ int make_w_map(smapb_handle* h, CUtensorMap* m, const __nv_bfloat16* ptr, int Ci
 // ------------------------------------------------------------------------------------------------
 // conv launch
 // ------------------------------------------------------------------------------------------------
-template <int BN, int NT>
-cudaError_t launch_conv_inst(const ConvParams& cp, int grid, cudaStream_t st, bool pdl) {
-    using Cfg = ConvCfg<BN, NT>;
+template <int BN, int NT, bool RING>
+cudaError_t launch_conv_inst2(const ConvParams& cp, int grid, cudaStream_t st, bool pdl) {
+    using Cfg = ConvCfg<BN, NT, RING>;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e =
-            cudaFuncSetAttribute(conv_tc_kernel<BN, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, NT, RING>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             Cfg::SMEM_BYTES);
         if (e != cudaSuccess) return e;
         configured = true;
     }
@@ -238,7 +246,12 @@ cudaError_t launch_conv_inst(const ConvParams& cp, int grid, cudaStream_t st, bo
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 1 : 0;
-    return cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, NT>, cp);
+    return cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, NT, RING>, cp);
+}
+template <int BN, int NT>
+cudaError_t launch_conv_inst(const ConvParams& cp, int grid, cudaStream_t st, bool pdl) {
+    return (cp.has_res + cp.n_post) ? launch_conv_inst2<BN, NT, true>(cp, grid, st, pdl)
+                                    : launch_conv_inst2<BN, NT, false>(cp, grid, st, pdl);
 }
 cudaError_t launch_conv(const ConvParams& cp, int block_n, int nterms, int sm_count, cudaStream_t st, bool pdl) {
     const int grid = cp.total_tiles < sm_count ? cp.total_tiles : sm_count;
@@ -727,6 +740,7 @@ int smapb_create(smapb_handle** out, int device, int max_batch, int in_h, int in
         delete h;
         return -10;
     }
+    if (cudaStreamCreate(&h->own_stream) != cudaSuccess) h->own_stream = nullptr;
     const char* aerr = nullptr;
     // association kernels stage whole planes in shared memory; larger maps are rejected at call time
     if (assoc_configure(h->h, h->w, &aerr) != 0) h->err = aerr ? aerr : "assoc_configure failed";
@@ -741,6 +755,8 @@ void smapb_destroy(smapb_handle* h) {
         if (kv.second->graph) cudaGraphExecDestroy(kv.second->graph);
         for (void* p : kv.second->allocs) cudaFree(p);
     }
+    for (auto& g : h->graphs) cudaGraphExecDestroy(g.exec);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
     for (auto& kv : h->layers) {
         cudaFree(kv.second.w_dev);
         cudaFree(kv.second.bias_dev);
@@ -775,6 +791,9 @@ int smapb_finalize_weights(smapb_handle* h, int precision) {
     // a new weight set invalidates cached plans (they hold tensor maps over the old weight buffers only if
     // buffers are re-allocated; buffers are reused in place, but the plane count may change)
     const int new_planes = precision == SMAPB_PREC_BF16X3 ? 2 : 1;
+    for (auto& g : h->graphs) cudaGraphExecDestroy(g.exec);
+    h->graphs.clear();
+    h->eager_runs.clear();
     if (new_planes != h->planes || !h->plans.empty()) {
         for (auto& kv : h->plans) {
             if (kv.second->graph) cudaGraphExecDestroy(kv.second->graph);
@@ -925,18 +944,9 @@ __global__ void flip_w_kernel(const float* __restrict__ in, float* __restrict__ 
     }
 }
 
-int smapb_infer_device(smapb_handle* h, const float* imgs, const double* scales, int B, int do_flip,
-                       smapb_record* records, void* stream) {
-    if (!h) return -1;
-    if (!h->finalized) return fail(h, -2, "smapb_infer_device: weights not finalized");
-    cudaSetDevice(h->device);
-    int rc = check_assoc(h, B);
-    if (rc) return rc;
-    cudaStream_t st = (cudaStream_t)stream;
-    Plan* plan = nullptr;
-    rc = build_plan(h, B, &plan);
-    if (rc) return rc;
-    rc = run_plan(h, plan, imgs, h->hm, h->detd, h->rootd, st);
+static int infer_body(smapb_handle* h, Plan* plan, const float* imgs, const double* scales, int B, int do_flip,
+                      smapb_record* records, cudaStream_t st) {
+    int rc = run_plan(h, plan, imgs, h->hm, h->detd, h->rootd, st);
     if (rc) return rc;
     const size_t hw = (size_t)h->h * h->w;
     if (do_flip) {
@@ -974,12 +984,66 @@ int smapb_infer_device(smapb_handle* h, const float* imgs, const double* scales,
     return 0;
 }
 
+int smapb_infer_device(smapb_handle* h, const float* imgs, const double* scales, int B, int do_flip,
+                       smapb_record* records, void* stream) {
+    if (!h) return -1;
+    if (!h->finalized) return fail(h, -2, "smapb_infer_device: weights not finalized");
+    cudaSetDevice(h->device);
+    int rc = check_assoc(h, B);
+    if (rc) return rc;
+    // The legacy default stream cannot be captured: run on the handle's own blocking stream instead (legacy-stream
+    // semantics keep it ordered with the caller's default-stream work on both sides).
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->own_stream;
+    Plan* plan = nullptr;
+    rc = build_plan(h, B, &plan);
+    if (rc) return rc;
+    do_flip = do_flip ? 1 : 0;
+    static const bool no_graph = getenv("SMAPB_NO_GRAPH") != nullptr;
+    // The whole path (~230 launches) is replayed from a CUDA graph: the first two calls for a (B, flip) run eagerly
+    // (lazy allocations, function attributes), then one graph per distinct input pointer pair is captured.  Results
+    // land in the handle's record buffer and are copied to the caller's pointer after the graph.
+    int& eager = h->eager_runs[{B, do_flip}];
+    if (no_graph || h->profiling || eager < 2 || st == nullptr) {
+        eager++;
+        return infer_body(h, plan, imgs, scales, B, do_flip, records, st);
+    }
+    smapb_handle::GraphEntry* ge = nullptr;
+    for (auto& g : h->graphs)
+        if (g.B == B && g.flip == do_flip && g.imgs == imgs && g.scales == scales) ge = &g;
+    if (!ge) {
+        if (h->graphs.size() >= 32) return infer_body(h, plan, imgs, scales, B, do_flip, records, st);
+        const int64_t launches_before = h->launches;
+        CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        rc = infer_body(h, plan, imgs, scales, B, do_flip, h->records_dev, st);
+        cudaGraph_t graph = nullptr;
+        cudaError_t ce = cudaStreamEndCapture(st, &graph);
+        h->launches = launches_before;
+        if (rc) {
+            if (graph) cudaGraphDestroy(graph);
+            return rc;
+        }
+        if (ce != cudaSuccess) return fail(h, -10, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce));
+        cudaGraphExec_t exec = nullptr;
+        ce = cudaGraphInstantiate(&exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ce != cudaSuccess) return fail(h, -10, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ce));
+        h->graphs.push_back({B, do_flip, imgs, scales, exec});
+        ge = &h->graphs.back();
+    }
+    CK(cudaGraphLaunch(ge->exec, st));
+    h->launches += (int64_t)plan->ops.size() * (do_flip ? 2 : 1) + 5 + (do_flip ? 1 : 0);
+    if (records != h->records_dev)
+        CK(cudaMemcpyAsync(records, h->records_dev, (size_t)B * sizeof(smapb_record), cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
 int smapb_infer_host(smapb_handle* h, const float* imgs_host, const double* scales_host, int B, int do_flip,
                      smapb_record* records_host, void* stream) {
     if (!h) return -1;
     if (B < 1 || B > h->max_batch) return fail(h, -1, "smapb_infer_host: B outside [1, max_batch]");
     cudaSetDevice(h->device);
-    cudaStream_t st = (cudaStream_t)stream;
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->own_stream;
+    stream = (void*)st;
     CK(cudaMemcpyAsync(h->imgs_dev, imgs_host, (size_t)B * 3 * h->in_h * h->in_w * 4, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(h->scales_dev, scales_host, (size_t)B * SMAPB_SCALE_LEN * 8, cudaMemcpyHostToDevice, st));
     int rc = smapb_infer_device(h, h->imgs_dev, h->scales_dev, B, do_flip, h->records_dev, stream);
