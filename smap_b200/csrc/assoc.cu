@@ -492,11 +492,27 @@ group_kernel(const float* __restrict__ peaks, const float* __restrict__ scores, 
                     }
                     __syncwarp();
                     const float bl = c_bone_length[i];
-                    for (int k1 = 0; k1 < P; k1++) {
-                        const float sscore = s_body[k1][src][2];
-                        if ((double)sscore < 1e-5) continue;  // association.cpp:190 (warp-uniform)
-                        const float sx = s_body[k1][src][0], sy = s_body[k1][src][1];
+                    // Score rows are prefetched one person ahead: the row index (remap of the source joint) and the
+                    // source scores are fixed for the whole limb, only `used` changes from person to person.
+                    auto load_row = [&](int k1, float(&row)[4]) {
                         const int rs = s_remap[src][k1];
+#pragma unroll
+                        for (int q = 0; q < 4; q++) {
+                            const int k2 = lane + 32 * q;
+                            row[q] = (k2 < dstSize) ? (flip ? sc[k2 * MAXP + rs] : sc[rs * MAXP + k2]) : -1.f;
+                        }
+                    };
+                    auto next_valid = [&](int k1) {
+                        while (k1 < P && (double)s_body[k1][src][2] < 1e-5) k1++;  // association.cpp:190
+                        return k1;
+                    };
+                    int k1 = next_valid(0);
+                    float cur[4], nxt[4];
+                    if (k1 < P) load_row(k1, cur);
+                    while (k1 < P) {
+                        const int k1n = next_valid(k1 + 1);
+                        if (k1n < P) load_row(k1n, nxt);
+                        const float sx = s_body[k1][src][0], sy = s_body[k1][src][1];
                         const float bone_dist =
                             __double2float_rn(__ddiv_rn(__dmul_rn(1.2, (double)bl), (double)s_sorted[k1]));
                         float best = 0.0f;
@@ -505,7 +521,7 @@ group_kernel(const float* __restrict__ peaks, const float* __restrict__ scores, 
                         for (int q = 0; q < 4; q++) {
                             const int k2 = lane + 32 * q;
                             if (k2 < dstSize && !used[k2]) {
-                                float score = flip ? sc[k2 * MAXP + rs] : sc[rs * MAXP + k2];
+                                float score = cur[q];
                                 if (dist_flag && score > 0) {
                                     const float ddx = __fsub_rn(sx, cx[q]), ddy = __fsub_rn(sy, cy[q]);
                                     const double d2 = __dadd_rn(__dmul_rn((double)ddx, (double)ddx),
@@ -540,6 +556,9 @@ group_kernel(const float* __restrict__ peaks, const float* __restrict__ scores, 
                             }
                             __syncwarp();
                         }
+                        k1 = k1n;
+#pragma unroll
+                        for (int q = 0; q < 4; q++) cur[q] = nxt[q];
                     }
                 }
             }

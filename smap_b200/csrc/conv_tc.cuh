@@ -30,6 +30,7 @@ namespace smapb {
 
 struct alignas(64) ConvParams {
     CUtensorMap tmA;  // activations (loads)
+    CUtensorMap tmA2; // second activation tensor of a K-concatenated 1x1 pair (conv3 + downsample), or unused
     CUtensorMap tmB;  // weights (loads)
     CUtensorMap tmO;  // output planes (stores, 32-channel boxes, SWIZZLE_64B)
     CUtensorMap tmR[3];  // epilogue input planes (loads, same geometry as tmO): [residual][post1][post2] as present
@@ -40,6 +41,7 @@ struct alignas(64) ConvParams {
     int Cout;  // channel stride of the output / residual tensors (elements)
     int ksize, stride, pad;
     int kchunks;  // Cin / 64
+    int kchunks2, stride2;  // K-concatenated second 1x1 input: Cin2 / 64 (0 = none) and its spatial stride
     int n_tiles;  // Cout_pad / BLOCK_N
     int total_tiles;
     // epilogue
@@ -198,6 +200,7 @@ __global__ void __launch_bounds__(384, 1) conv_tc_kernel(const __grid_constant__
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&p.tmA);
         tma_prefetch_desc(&p.tmB);
+        if (p.kchunks2) tma_prefetch_desc(&p.tmA2);
         if (tma_out) tma_prefetch_desc(&p.tmO);
         for (int e = 0; e < n_extra; e++) tma_prefetch_desc(&p.tmR[e]);
     }
@@ -227,7 +230,8 @@ __global__ void __launch_bounds__(384, 1) conv_tc_kernel(const __grid_constant__
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int num_kb = p.ksize * p.ksize * p.kchunks;
+    const int num_kb1 = p.ksize * p.ksize * p.kchunks;
+    const int num_kb = num_kb1 + p.kchunks2;
     const int tiles_per_img = p.tiles_x * p.tiles_y;
     const int tw = 1 << p.tw_log2;
 
@@ -245,17 +249,28 @@ __global__ void __launch_bounds__(384, 1) conv_tc_kernel(const __grid_constant__
                 const int x_in0 = (tx << p.tw_log2) * p.stride - p.pad;
                 const int y_in0 = ty * p.th * p.stride - p.pad;
                 for (int kb = 0; kb < num_kb; kb++) {
-                    const int tap = kb / p.kchunks, kc = kb - tap * p.kchunks;
-                    const int ky = tap / p.ksize, kx = tap - ky * p.ksize;
                     mbar_wait(&empty_bar[stage], phase ^ 1u);
                     const uint32_t sbase = ring + stage * Cfg::STAGE_BYTES;
                     mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+                    if (kb < num_kb1) {
+                        const int tap = kb / p.kchunks, kc = kb - tap * p.kchunks;
+                        const int ky = tap / p.ksize, kx = tap - ky * p.ksize;
 #pragma unroll
-                    for (int t = 0; t < Cfg::TA; t++) {
-                        tma_load_5d(sbase + t * Cfg::A_BYTES, &p.tmA, &full_bar[stage], kc * 64, x_in0 + kx, y_in0 + ky,
-                                    img, t);
-                        tma_load_4d(sbase + Cfg::TA * Cfg::A_BYTES + t * Cfg::B_BYTES, &p.tmB, &full_bar[stage],
-                                    kc * 64, nt * BLOCK_N, tap, t);
+                        for (int t = 0; t < Cfg::TA; t++) {
+                            tma_load_5d(sbase + t * Cfg::A_BYTES, &p.tmA, &full_bar[stage], kc * 64, x_in0 + kx,
+                                        y_in0 + ky, img, t);
+                            tma_load_4d(sbase + Cfg::TA * Cfg::A_BYTES + t * Cfg::B_BYTES, &p.tmB, &full_bar[stage],
+                                        kc * 64, nt * BLOCK_N, tap, t);
+                        }
+                    } else {  // K-concatenated second input (1x1, own stride): weight columns continue after Cin
+                        const int kc2 = kb - num_kb1;
+#pragma unroll
+                        for (int t = 0; t < Cfg::TA; t++) {
+                            tma_load_5d(sbase + t * Cfg::A_BYTES, &p.tmA2, &full_bar[stage], kc2 * 64,
+                                        (tx << p.tw_log2) * p.stride2, ty * p.th * p.stride2, img, t);
+                            tma_load_4d(sbase + Cfg::TA * Cfg::A_BYTES + t * Cfg::B_BYTES, &p.tmB, &full_bar[stage],
+                                        (p.kchunks + kc2) * 64, nt * BLOCK_N, 0, t);
+                        }
                     }
                     if (++stage == STAGES) {
                         stage = 0;

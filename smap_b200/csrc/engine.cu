@@ -69,6 +69,7 @@ struct ActF32 {
 struct ConvLayer {
     std::string name;
     int Cin = 0, Cout = 0, Cout_pad = 0, k = 1, stride = 1, pad = 0, relu = 0;
+    int Cin2 = 0, stride2 = 1;  // K-concatenated second 1x1 input (weights hold Cin + Cin2 columns)
     __nv_bfloat16* w_dev = nullptr;  // [T][taps][Cout_pad][Cin]
     float* bias_dev = nullptr;       // [Cout_pad]
 };
@@ -129,6 +130,7 @@ struct smapb_handle {
     float* scratch_rootd = nullptr;
     double* scales_dev = nullptr;
     smapb_record* records_dev = nullptr;
+    bool use_pdl = getenv("SMAPB_PDL") != nullptr;  // programmatic dependent launch between conv kernels
     cudaStream_t own_stream = nullptr;  // blocking stream used when the caller passes the legacy default stream
     struct GraphEntry {
         int B, flip;
@@ -271,13 +273,16 @@ cudaError_t launch_conv(const ConvParams& cp, int block_n, int nterms, int sm_co
 
 // Fill a ConvParams for `layer` applied to `in`, producing (out | out_f32).
 int setup_conv(smapb_handle* h, const ConvLayer& L, const Act& in, const Act* res, const Act* post1, const Act* post2,
-               const Act* out, const ActF32* outf, int relu, ConvParams* cp, int* block_n_out, double* flops_out) {
+               const Act* out, const ActF32* outf, int relu, ConvParams* cp, int* block_n_out, double* flops_out,
+               const Act* in2 = nullptr) {
     const int Ho = (in.H + 2 * L.pad - L.k) / L.stride + 1, Wo = (in.W + 2 * L.pad - L.k) / L.stride + 1;
     const int N = in.N;
     if (in.C != L.Cin) return fail(h, -30, "conv " + L.name + ": Cin mismatch");
     if (L.Cin % 64 != 0) return fail(h, -30, "conv " + L.name + ": Cin must be a multiple of 64");
     memset(cp, 0, sizeof(*cp));
-    const bool flat = (L.k == 1 && L.stride == 1);
+    if ((L.Cin2 != 0) != (in2 != nullptr)) return fail(h, -30, "conv " + L.name + ": second input mismatch");
+    if (in2 && (in2->C != L.Cin2 || L.k != 1 || L.stride != 1)) return fail(h, -30, "conv " + L.name + ": bad fused pair");
+    const bool flat = (L.k == 1 && L.stride == 1 && (!in2 || L.stride2 == 1));
     int tw, th, tiles_x, tiles_y, nimg;
     int rc;
     if (flat) {
@@ -290,13 +295,15 @@ int setup_conv(smapb_handle* h, const ConvLayer& L, const Act& in, const Act* re
         cp->Hout = 1;
         cp->Wout = (int)M;
         rc = make_act_map(h, &cp->tmA, in.ptr, in.C, M, 1, 1, h->planes, in.plane(), 128, 1, 1);
+        if (!rc && in2) rc = make_act_map(h, &cp->tmA2, in2->ptr, in2->C, M, 1, 1, h->planes, in2->plane(), 128, 1, 1);
     } else {
         // pick the patch shape with the fewest wasted rows
         double best = -1;
         tw = 16;
+        const int smax = in2 ? (L.stride2 > L.stride ? L.stride2 : L.stride) : L.stride;
         for (int c = 128; c >= 1; c >>= 1) {
             const int t_h = 128 / c;
-            if (c * L.stride > 256 || t_h * L.stride > 256) continue;
+            if (c * smax > 256 || t_h * smax > 256) continue;
             const double util = ((double)Wo * Ho) / ((double)((Wo + c - 1) / c) * c * ((Ho + t_h - 1) / t_h) * t_h);
             if (util > best + 1e-9) {
                 best = util;
@@ -311,6 +318,9 @@ int setup_conv(smapb_handle* h, const ConvLayer& L, const Act& in, const Act* re
         cp->Wout = Wo;
         rc = make_act_map(h, &cp->tmA, in.ptr, in.C, in.W, in.H, N, h->planes, in.plane(), tw * L.stride,
                           th * L.stride, L.stride);
+        if (!rc && in2)
+            rc = make_act_map(h, &cp->tmA2, in2->ptr, in2->C, in2->W, in2->H, N, h->planes, in2->plane(),
+                              tw * L.stride2, th * L.stride2, L.stride2);
     }
     if (rc) return rc;
     int twl = 0;
@@ -326,7 +336,7 @@ int setup_conv(smapb_handle* h, const ConvLayer& L, const Act& in, const Act* re
     const int cands[4] = {256, 128, 64, 32};
     // 256-wide tiles leave room for only single-buffered epilogue staging: keep them for long-K layers without
     // a residual stream (compute-bound), use <= 128 elsewhere
-    const bool allow256 = (h->nterms == 1) && (res == nullptr) && (L.Cin * L.k * L.k >= 512);
+    const bool allow256 = (h->nterms == 1) && (res == nullptr) && ((L.Cin + L.Cin2) * L.k * L.k >= 512);
     for (int c : cands) {
         if (L.Cout_pad % c) continue;
         if (c == 256 && !allow256) continue;
@@ -347,6 +357,8 @@ int setup_conv(smapb_handle* h, const ConvLayer& L, const Act& in, const Act* re
     cp->stride = L.stride;
     cp->pad = L.pad;
     cp->kchunks = L.Cin / 64;
+    cp->kchunks2 = L.Cin2 / 64;
+    cp->stride2 = L.stride2;
     cp->n_tiles = L.Cout_pad / bn;
     cp->total_tiles = (int)(m_tiles * cp->n_tiles);
     cp->bias = L.bias_dev;
@@ -367,7 +379,7 @@ int setup_conv(smapb_handle* h, const ConvLayer& L, const Act& in, const Act* re
                 cp->one_group = 1;
         }
     }
-    rc = make_w_map(h, &cp->tmB, L.w_dev, L.Cin, L.Cout_pad, L.k * L.k, h->planes, bn);
+    rc = make_w_map(h, &cp->tmB, L.w_dev, L.Cin + L.Cin2, L.Cout_pad, L.k * L.k, h->planes, bn);
     if (rc) return rc;
     // epilogue tiles: 32 channels x (tw x th) pixels of the output / residual planes
     int n_in = 0;
@@ -382,7 +394,7 @@ int setup_conv(smapb_handle* h, const ConvLayer& L, const Act& in, const Act* re
         if (rc) return rc;
     }
     *block_n_out = bn;
-    if (flops_out) *flops_out = 2.0 * N * Ho * Wo * (double)L.Cout * L.Cin * L.k * L.k;
+    if (flops_out) *flops_out = 2.0 * N * Ho * Wo * (double)L.Cout * (L.Cin * L.k * L.k + L.Cin2);
     return 0;
 }
 
@@ -421,14 +433,15 @@ int fold_unit(smapb_handle* h, const std::string& name, std::vector<float>* wf, 
 
 int upload_conv_layer(smapb_handle* h, ConvLayer& L, const std::vector<float>& wf, const std::vector<float>& bf) {
     const int taps = L.k * L.k;
-    const size_t plane = (size_t)taps * L.Cout_pad * L.Cin;
+    const int cin = L.Cin + L.Cin2;  // wf holds [Cout][Cin + Cin2][taps] (taps == 1 for fused pairs)
+    const size_t plane = (size_t)taps * L.Cout_pad * cin;
     std::vector<uint16_t> host(plane * h->planes, 0);
     for (int co = 0; co < L.Cout; co++)
-        for (int ci = 0; ci < L.Cin; ci++)
+        for (int ci = 0; ci < cin; ci++)
             for (int t = 0; t < taps; t++) {
-                const float v = wf[((size_t)co * L.Cin + ci) * taps + t];
+                const float v = wf[((size_t)co * cin + ci) * taps + t];
                 const uint16_t hi = f32_to_bf16_rn(v);
-                const size_t o = ((size_t)t * L.Cout_pad + co) * L.Cin + ci;
+                const size_t o = ((size_t)t * L.Cout_pad + co) * cin + ci;
                 host[o] = hi;
                 if (h->planes == 2) host[plane + o] = f32_to_bf16_rn(v - bf16_to_f32(hi));
             }
@@ -487,7 +500,7 @@ struct PlanBuilder {
         return &it->second;
     }
     Act conv(const std::string& name, const Act& in, int relu, const Act* res = nullptr, const Act* p1 = nullptr,
-             const Act* p2 = nullptr) {
+             const Act* p2 = nullptr, const Act* in2 = nullptr) {
         Act out;
         if (rc) return out;
         const ConvLayer* L = layer(name);
@@ -497,7 +510,7 @@ struct PlanBuilder {
         if (rc) return out;
         Op op;
         op.kind = OP_CONV;
-        rc = setup_conv(h, *L, in, res, p1, p2, &out, nullptr, relu, &op.cp, &op.block_n, &op.flops);
+        rc = setup_conv(h, *L, in, res, p1, p2, &out, nullptr, relu, &op.cp, &op.block_n, &op.flops, in2);
         plan->ops.push_back(op);
         plan->n_conv++;
         plan->conv_flops += op.flops;
@@ -559,11 +572,15 @@ int build_plan(smapb_handle* h, int B, Plan** out_plan) {
                 const std::string p = pre + "downsample.layer" + std::to_string(li + 1) + "." + std::to_string(b) + ".";
                 Act o1 = pb.conv(p + "conv_bn_relu1", t, 1);
                 Act o2 = pb.conv(p + "conv_bn_relu2", o1, 1);
-                Act idn = t;
-                if (b == 0) idn = pb.conv(p + "downsample", t, 0);
                 const bool last = (b == LAYERS[li] - 1) && s > 0;
-                // out = relu(conv3 + x) [ + skip1 + skip2 ]   (model/smap.py:74-75,143)
-                t = pb.conv(p + "conv_bn_relu3", o2, 1, &idn, last ? &skip1[li] : nullptr, last ? &skip2[li] : nullptr);
+                if (b == 0) {
+                    // relu(conv3(o2) + downsample(x)) as one K-concatenated GEMM
+                    t = pb.conv(p + "fused_conv3_downsample", o2, 1, nullptr, nullptr, nullptr, &t);
+                } else {
+                    // out = relu(conv3 + x) [ + skip1 + skip2 ]   (model/smap.py:74-75,143)
+                    t = pb.conv(p + "conv_bn_relu3", o2, 1, &t, last ? &skip1[li] : nullptr,
+                                last ? &skip2[li] : nullptr);
+                }
             }
             feats[li] = t;
         }
@@ -656,7 +673,7 @@ int run_plan(smapb_handle* h, Plan* plan, const float* imgs, float* hm2d, float*
                 prof_mark(h, PK_STEM, st, "maxpool");
                 break;
             case OP_CONV:
-                CK(launch_conv(op.cp, op.block_n, h->nterms, h->sm_count, st, false));
+                CK(launch_conv(op.cp, op.block_n, h->nterms, h->sm_count, st, h->use_pdl));
                 if (h->profiling) {
                     char d[160];
                     snprintf(d, sizeof d, "conv k%d s%d cin%d cout%d out%dx%d bn%d tiles%d", op.cp.ksize, op.cp.stride,
@@ -817,11 +834,16 @@ int smapb_finalize_weights(smapb_handle* h, int precision) {
             units.push_back(k.substr(0, k.size() - suf.size()));
     }
     if (units.empty()) return fail(h, -40, "no weights loaded");
+    std::map<std::string, std::pair<std::vector<float>, std::vector<float>>> folded;  // 1x1 units of bottleneck pairs
     for (const std::string& name : units) {
         std::vector<float> wf, bf;
         int Cout, Cin, k;
         int rc = fold_unit(h, name, &wf, &bf, &Cout, &Cin, &k);
         if (rc) return rc;
+        if (name.find(".downsample.layer") != std::string::npos &&
+            (name.find(".0.conv_bn_relu3") != std::string::npos ||
+             (name.size() > 13 && name.compare(name.size() - 13, 13, ".0.downsample") == 0)))
+            folded[name] = {wf, bf};
         if (name == "top.conv") {
             if (Cin != 3 || Cout != 64 || k != 7) return fail(h, -40, "top.conv must be 3->64 7x7");
             std::vector<float> w2(147 * 64);
@@ -862,6 +884,37 @@ int smapb_finalize_weights(smapb_handle* h, int precision) {
         }
         int rc2 = upload_conv_layer(h, L, wf, bf);
         if (rc2) return rc2;
+    }
+    // First bottleneck of every layer: out = relu(conv3(o2) + downsample(x)) (model/smap.py:70-75) is ONE GEMM over
+    // the K-concatenated inputs [o2 | x] with weights [W3 | Wds] and bias b3 + bds: the downsample tensor is never
+    // written to HBM and never re-read as a residual.
+    for (auto& kv : folded) {
+        const std::string& n3 = kv.first;
+        const size_t pos = n3.find(".0.conv_bn_relu3");
+        if (pos == std::string::npos) continue;
+        const std::string base = n3.substr(0, pos), nds = base + ".0.downsample";
+        auto ids = folded.find(nds);
+        if (ids == folded.end()) return fail(h, -40, "missing downsample unit for " + n3);
+        const ConvLayer& L3 = h->layers[n3];
+        const ConvLayer& Lds = h->layers[nds];
+        ConvLayer& F = h->layers[base + ".0.fused_conv3_downsample"];
+        F.name = base + ".0.fused_conv3_downsample";
+        F.Cin = L3.Cin;
+        F.Cin2 = Lds.Cin;
+        F.stride2 = Lds.stride;
+        F.Cout = L3.Cout;
+        F.Cout_pad = L3.Cout_pad;
+        F.k = 1, F.stride = 1, F.pad = 0;
+        const int cin = F.Cin + F.Cin2;
+        std::vector<float> wf((size_t)F.Cout * cin), bf(F.Cout);
+        for (int co = 0; co < F.Cout; co++) {
+            for (int ci = 0; ci < F.Cin; ci++) wf[(size_t)co * cin + ci] = kv.second.first[(size_t)co * F.Cin + ci];
+            for (int ci = 0; ci < F.Cin2; ci++)
+                wf[(size_t)co * cin + F.Cin + ci] = ids->second.first[(size_t)co * F.Cin2 + ci];
+            bf[co] = kv.second.second[co] + ids->second.second[co];
+        }
+        int rc3 = upload_conv_layer(h, F, wf, bf);
+        if (rc3) return rc3;
     }
     if (!h->stem_w) return fail(h, -40, "top.conv weights missing");
     h->finalized = true;
