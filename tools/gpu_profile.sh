@@ -1,0 +1,12 @@
+#!/bin/bash
+# ncu evidence for profiles/: (1) launch list with per-launch device time for one bench step, (2) --set full capture of the
+# dominant kernel (conv_tc) on representative launches.  Numbers printed under ncu are never bench values.
+mkdir -p gpurun_out
+export SMAPB_NO_GRAPH=1
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 1400 -c 460 --csv --log-file gpurun_out/launches.csv \
+    python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
+echo "launch list rc=$?"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:conv_tc -s 230 -c 40 -o gpurun_out/prof_conv \
+    python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
+echo "full capture rc=$?"
+ls -la gpurun_out | tail -8
