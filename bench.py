@@ -101,8 +101,8 @@ def cpu_oracle_fps(frames, threads=None, seed=1):
 
     from oracle import assoc, lift_numpy, smap_torch
 
-    if threads:
-        torch.set_num_threads(threads)
+    # all host cores (torchrun exports OMP_NUM_THREADS=1, which would starve the CPU baseline)
+    torch.set_num_threads(threads or len(os.sched_getaffinity(0)))
     sd = smap_torch.make_state_dict(0, "identity")
     x = smap_torch.make_input(frames, IN_H, IN_W, seed=seed)
     scale = lift_numpy.default_scale(1920, 1080)

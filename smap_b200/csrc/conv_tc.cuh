@@ -53,6 +53,10 @@ struct alignas(64) ConvParams {
     long long plane_stride;  // elements between the hi and lo planes (= N*H*W*Cout)
     int relu;
     int one_group;  // debug: epilogue group 0 takes every chunk
+    // fused bilinear residual (Upsample_unit, model/smap.py:211-217): tmR[0] is a low-resolution tensor [N,Hi,Wi,C];
+    // the ring carries the (ph x pw)-pixel patch under each output tile and the epilogue interpolates
+    // (align_corners=True) before the ReLU.  up_mode = 0: plain residual.
+    int up_mode, up_Hi, up_Wi, up_pw, up_ph;
 };
 
 // ---- tcgen05 / TMA PTX wrappers -----------------------------------------------------------------
@@ -143,6 +147,10 @@ __device__ __forceinline__ void sts_v4(uint32_t addr, uint4 v) {
 }
 // byte offset of 16-byte chunk j (0..3) of row r in a [128 rows x 64 B] SWIZZLE_64B box
 __device__ __forceinline__ uint32_t sw64_off(int r, int j) { return (uint32_t)(r * 64 + ((j ^ ((r >> 1) & 3)) << 4)); }
+
+// ATen bilinear, align_corners=True: src = dst * (in-1)/(out-1) in fp32; i0 = (int)src
+__device__ __forceinline__ float up_scale(int in, int out) { return out > 1 ? (float)(in - 1) / (float)(out - 1) : 0.f; }
+__device__ __forceinline__ int up_src_index(int dst, int in, int out) { return (int)(up_scale(in, out) * (float)dst); }
 
 __device__ __forceinline__ uint4 ldg_v4(const void* p) {
     uint4 r;
@@ -340,11 +348,18 @@ __global__ void __launch_bounds__(384, 1) conv_tc_kernel(const __grid_constant__
                         const int m = cnt[g]++;
                         const int slot = g * Cfg::SPG + (m % Cfg::SPG);
                         mbar_wait(&rempty_bar[slot], ((uint32_t)(m / Cfg::SPG) & 1u) ^ 1u);
-                        mbar_arrive_expect_tx(&rfull_bar[slot], Cfg::SLOT_BYTES);
+                        int cx = tx << p.tw_log2, cy = ty * p.th;
+                        uint32_t bytes = Cfg::SLOT_BYTES;
+                        if (p.up_mode && e == 0) {  // low-resolution patch under this tile
+                            cx = up_src_index(cx, p.up_Wi, p.Wout);
+                            cy = up_src_index(cy, p.up_Hi, p.Hout);
+                            bytes = (uint32_t)(p.up_pw * p.up_ph * 64 * Cfg::TA);
+                        }
+                        mbar_arrive_expect_tx(&rfull_bar[slot], bytes);
 #pragma unroll
                         for (int t = 0; t < Cfg::TA; t++)
                             tma_load_5d(res_stage + slot * Cfg::SLOT_BYTES + t * Cfg::CHUNK_BYTES, &p.tmR[e],
-                                        &rfull_bar[slot], nt * BLOCK_N + c * 32, tx << p.tw_log2, ty * p.th, img, t);
+                                        &rfull_bar[slot], nt * BLOCK_N + c * 32, cx, cy, img, t);
                     }
                 }
             }
@@ -403,7 +418,43 @@ __global__ void __launch_bounds__(384, 1) conv_tc_kernel(const __grid_constant__
                     }
                 };
                 uint4 rh[4], rl[4];
-                if (RING && p.has_res) ring_fetch(rh, rl);
+                float upv[32];
+                if (RING && p.has_res && !p.up_mode) ring_fetch(rh, rl);
+                if (RING && p.up_mode) {
+                    // bilinear x2 of the low-resolution patch in the ring slot (weights as ATen computes them)
+                    const int m = rcnt++;
+                    const int rslot = g * Cfg::SPG + (m % Cfg::SPG);
+                    mbar_wait(&rfull_bar[rslot], (uint32_t)(m / Cfg::SPG) & 1u);
+                    const uint32_t rb = res_stage + rslot * Cfg::SLOT_BYTES;
+                    const int pyc = min(py, p.Hout - 1), pxc = min(px, p.Wout - 1);  // clipped rows are never stored
+                    const float sy = up_scale(p.up_Hi, p.Hout) * (float)pyc, sx = up_scale(p.up_Wi, p.Wout) * (float)pxc;
+                    const int y0i = (int)sy, x0i = (int)sx;
+                    const int y1i = y0i + (y0i < p.up_Hi - 1 ? 1 : 0), x1i = x0i + (x0i < p.up_Wi - 1 ? 1 : 0);
+                    const float hy1 = sy - (float)y0i, hy0 = 1.f - hy1, wx1 = sx - (float)x0i, wx0 = 1.f - wx1;
+                    const int oy0 = up_src_index(ty * p.th, p.up_Hi, p.Hout), ox0 = up_src_index(tx << p.tw_log2, p.up_Wi, p.Wout);
+                    const int r00 = (y0i - oy0) * p.up_pw + (x0i - ox0), r01 = (y0i - oy0) * p.up_pw + (x1i - ox0);
+                    const int r10 = (y1i - oy0) * p.up_pw + (x0i - ox0), r11 = (y1i - oy0) * p.up_pw + (x1i - ox0);
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        float q[4][8];
+                        const int rr[4] = {r00, r01, r10, r11};
+#pragma unroll
+                        for (int k = 0; k < 4; k++) {
+                            const uint4 hh = lds_v4(rb + sw64_off(rr[k], j));
+                            const uint4 ll = (NTERMS == 3) ? lds_v4(rb + Cfg::CHUNK_BYTES + sw64_off(rr[k], j)) : make_uint4(0, 0, 0, 0);
+                            const uint32_t h[4] = {hh.x, hh.y, hh.z, hh.w}, l[4] = {ll.x, ll.y, ll.z, ll.w};
+#pragma unroll
+                            for (int e = 0; e < 4; e++) {
+                                q[k][2 * e] = bf16lo_to_f(h[e]) + bf16lo_to_f(l[e]);
+                                q[k][2 * e + 1] = bf16hi_to_f(h[e]) + bf16hi_to_f(l[e]);
+                            }
+                        }
+#pragma unroll
+                        for (int e = 0; e < 8; e++)
+                            upv[8 * j + e] = hy0 * (wx0 * q[0][e] + wx1 * q[1][e]) + hy1 * (wx0 * q[2][e] + wx1 * q[3][e]);
+                    }
+                    mbar_arrive(&rempty_bar[rslot]);
+                }
                 tmem_ld_wait();
                 float v[32];
 #pragma unroll
@@ -414,7 +465,11 @@ __global__ void __launch_bounds__(384, 1) conv_tc_kernel(const __grid_constant__
                     v[4 * j + 2] = __uint_as_float(acc_r[4 * j + 2]) + b.z;
                     v[4 * j + 3] = __uint_as_float(acc_r[4 * j + 3]) + b.w;
                 }
-                if (RING && p.has_res) add_planes(v, rh, rl);
+                if (RING && p.has_res && !p.up_mode) add_planes(v, rh, rl);
+                if (RING && p.up_mode) {
+#pragma unroll
+                    for (int j = 0; j < 32; j++) v[j] += upv[j];
+                }
                 if (p.relu) {
 #pragma unroll
                     for (int j = 0; j < 32; j++) v[j] = fmaxf(v[j], 0.f);

@@ -28,16 +28,20 @@ cudaError_t launch_f32_to_split(const float* x, __nv_bfloat16* out, long long n,
 // Input fp32 NCHW [N,3,H,W]; output split-bf16 NHWC [N,H/2,W/2,64].
 // CTA = 8 x 32 output pixels x 64 channels; thread = one pixel, 4 passes of 16 channels.
 // ---------------------------------------------------------------------------------------------
-constexpr int ST_TW = 32, ST_TH = 8;
-constexpr int ST_PW = ST_TW * 2 + 5, ST_PH = ST_TH * 2 + 5;  // input patch 69 x 21
+constexpr int ST_TW = 128, ST_TH = 8;                         // output tile per CTA
+constexpr int ST_PX = 4;                                        // adjacent output pixels per thread
+constexpr int ST_PW = ST_TW * 2 + 5, ST_PH = ST_TH * 2 + 5;     // input patch 261 x 21
+constexpr int ST_PWP = ST_PW + 3;                               // padded row pitch
 
+// thread = 4 adjacent output pixels x 16 channels (4 passes over the channel groups): per (ky, ci) row the 13 input
+// values and the 7x16 weights are loaded once and feed 448 FFMAs (11 FFMA per shared-memory load).
 __global__ void __launch_bounds__(256, 2)
 stem_kernel(const float* __restrict__ x, const float* __restrict__ wgt /*[147][64] (ky,kx,ci) x co*/,
             const float* __restrict__ bias, int H, int W, __nv_bfloat16* __restrict__ out, long long plane_stride,
             int terms) {
     extern __shared__ __align__(16) float stem_smem[];
-    float* s_w = stem_smem;                                                            // [147*64]
-    float(*s_in)[ST_PH][ST_PW + 1] = reinterpret_cast<float(*)[ST_PH][ST_PW + 1]>(stem_smem + 147 * 64);  // [3][..][..]
+    float* s_w = stem_smem;                   // [147*64]
+    float* s_in = stem_smem + 147 * 64;       // [3][ST_PH][ST_PWP]
     const int Ho = H / 2, Wo = W / 2;
     const int n = blockIdx.z;
     const int oy0 = blockIdx.y * ST_TH, ox0 = blockIdx.x * ST_TW;
@@ -50,55 +54,71 @@ stem_kernel(const float* __restrict__ x, const float* __restrict__ wgt /*[147][6
         const int iy = iy0 + py, ix = ix0 + px;
         float v = 0.f;
         if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = x[(((size_t)n * 3 + c) * H + iy) * W + ix];
-        s_in[c][py][px] = v;
+        s_in[(c * ST_PH + py) * ST_PWP + px] = v;
     }
     __syncthreads();
-    const int ty = threadIdx.x / ST_TW, tx = threadIdx.x % ST_TW;
-    const int oy = oy0 + ty, ox = ox0 + tx;
-    const bool valid = oy < Ho && ox < Wo;
-    const size_t obase = (((size_t)n * Ho + oy) * Wo + ox) * 64;
+    const int ty = threadIdx.x / (ST_TW / ST_PX), tx = (threadIdx.x % (ST_TW / ST_PX)) * ST_PX;
+    const int oy = oy0 + ty;
 #pragma unroll 1
     for (int cg = 0; cg < 4; cg++) {
-        float acc[16];
+        float acc[ST_PX][16];
 #pragma unroll
-        for (int j = 0; j < 16; j++) acc[j] = 0.f;
+        for (int p = 0; p < ST_PX; p++)
+#pragma unroll
+            for (int j = 0; j < 16; j++) acc[p][j] = 0.f;
+#pragma unroll 1
         for (int ky = 0; ky < 7; ky++) {
 #pragma unroll
-            for (int kx = 0; kx < 7; kx++) {
+            for (int c = 0; c < 3; c++) {
+                float in[16];  // 13 used; 4 x LDS.128 (row pitch and tx*2 keep 16-byte alignment)
+                const float4* row4 = reinterpret_cast<const float4*>(s_in + (c * ST_PH + ty * 2 + ky) * ST_PWP + tx * 2);
 #pragma unroll
-                for (int c = 0; c < 3; c++) {
-                    const float v = s_in[c][ty * 2 + ky][tx * 2 + kx];
+                for (int i = 0; i < 4; i++) {
+                    const float4 q = row4[i];
+                    in[4 * i] = q.x, in[4 * i + 1] = q.y, in[4 * i + 2] = q.z, in[4 * i + 3] = q.w;
+                }
+#pragma unroll
+                for (int kx = 0; kx < 7; kx++) {
                     const float4* wp = reinterpret_cast<const float4*>(&s_w[((ky * 7 + kx) * 3 + c) * 64 + cg * 16]);
 #pragma unroll
                     for (int j = 0; j < 4; j++) {
                         const float4 w4 = wp[j];
-                        acc[4 * j + 0] = fmaf(v, w4.x, acc[4 * j + 0]);
-                        acc[4 * j + 1] = fmaf(v, w4.y, acc[4 * j + 1]);
-                        acc[4 * j + 2] = fmaf(v, w4.z, acc[4 * j + 2]);
-                        acc[4 * j + 3] = fmaf(v, w4.w, acc[4 * j + 3]);
+#pragma unroll
+                        for (int p = 0; p < ST_PX; p++) {
+                            const float v = in[2 * p + kx];
+                            acc[p][4 * j + 0] = fmaf(v, w4.x, acc[p][4 * j + 0]);
+                            acc[p][4 * j + 1] = fmaf(v, w4.y, acc[p][4 * j + 1]);
+                            acc[p][4 * j + 2] = fmaf(v, w4.z, acc[p][4 * j + 2]);
+                            acc[p][4 * j + 3] = fmaf(v, w4.w, acc[p][4 * j + 3]);
+                        }
                     }
                 }
             }
         }
-        if (valid) {
-            uint32_t hw_[8], lw_[8];
 #pragma unroll
-            for (int j = 0; j < 8; j++) {
-                const float a = fmaxf(acc[2 * j] + bias[cg * 16 + 2 * j], 0.f);
-                const float b = fmaxf(acc[2 * j + 1] + bias[cg * 16 + 2 * j + 1], 0.f);
-                __nv_bfloat16 ah, al, bh, bl;
-                split_bf16(a, ah, al);
-                split_bf16(b, bh, bl);
-                hw_[j] = pack_bf16x2(ah, bh);
-                lw_[j] = pack_bf16x2(al, bl);
-            }
-            uint4* oh = reinterpret_cast<uint4*>(out + obase + cg * 16);
-            oh[0] = make_uint4(hw_[0], hw_[1], hw_[2], hw_[3]);
-            oh[1] = make_uint4(hw_[4], hw_[5], hw_[6], hw_[7]);
-            if (terms == 2) {
-                uint4* ol = reinterpret_cast<uint4*>(out + plane_stride + obase + cg * 16);
-                ol[0] = make_uint4(lw_[0], lw_[1], lw_[2], lw_[3]);
-                ol[1] = make_uint4(lw_[4], lw_[5], lw_[6], lw_[7]);
+        for (int p = 0; p < ST_PX; p++) {
+            const int ox = ox0 + tx + p;
+            if (oy < Ho && ox < Wo) {
+                const size_t obase = (((size_t)n * Ho + oy) * Wo + ox) * 64;
+                uint32_t hw_[8], lw_[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const float a = fmaxf(acc[p][2 * j] + bias[cg * 16 + 2 * j], 0.f);
+                    const float b = fmaxf(acc[p][2 * j + 1] + bias[cg * 16 + 2 * j + 1], 0.f);
+                    __nv_bfloat16 ah, al, bh, bl;
+                    split_bf16(a, ah, al);
+                    split_bf16(b, bh, bl);
+                    hw_[j] = pack_bf16x2(ah, bh);
+                    lw_[j] = pack_bf16x2(al, bl);
+                }
+                uint4* oh = reinterpret_cast<uint4*>(out + obase + cg * 16);
+                oh[0] = make_uint4(hw_[0], hw_[1], hw_[2], hw_[3]);
+                oh[1] = make_uint4(hw_[4], hw_[5], hw_[6], hw_[7]);
+                if (terms == 2) {
+                    uint4* ol = reinterpret_cast<uint4*>(out + plane_stride + obase + cg * 16);
+                    ol[0] = make_uint4(lw_[0], lw_[1], lw_[2], lw_[3]);
+                    ol[1] = make_uint4(lw_[4], lw_[5], lw_[6], lw_[7]);
+                }
             }
         }
     }
@@ -108,7 +128,7 @@ cudaError_t launch_stem(const float* x, const float* wgt, const float* bias, int
                         long long plane_stride, int terms, cudaStream_t st) {
     const int Ho = H / 2, Wo = W / 2;
     dim3 grid((Wo + ST_TW - 1) / ST_TW, (Ho + ST_TH - 1) / ST_TH, N);
-    constexpr int smem = (147 * 64 + 3 * ST_PH * (ST_PW + 1)) * 4;
+    constexpr int smem = (147 * 64 + 3 * ST_PH * ST_PWP) * 4;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(stem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);

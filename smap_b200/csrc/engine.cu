@@ -274,7 +274,7 @@ cudaError_t launch_conv(const ConvParams& cp, int block_n, int nterms, int sm_co
 // Fill a ConvParams for `layer` applied to `in`, producing (out | out_f32).
 int setup_conv(smapb_handle* h, const ConvLayer& L, const Act& in, const Act* res, const Act* post1, const Act* post2,
                const Act* out, const ActF32* outf, int relu, ConvParams* cp, int* block_n_out, double* flops_out,
-               const Act* in2 = nullptr) {
+               const Act* in2 = nullptr, const Act* up = nullptr) {
     const int Ho = (in.H + 2 * L.pad - L.k) / L.stride + 1, Wo = (in.W + 2 * L.pad - L.k) / L.stride + 1;
     const int N = in.N;
     if (in.C != L.Cin) return fail(h, -30, "conv " + L.name + ": Cin mismatch");
@@ -282,7 +282,8 @@ int setup_conv(smapb_handle* h, const ConvLayer& L, const Act& in, const Act* re
     memset(cp, 0, sizeof(*cp));
     if ((L.Cin2 != 0) != (in2 != nullptr)) return fail(h, -30, "conv " + L.name + ": second input mismatch");
     if (in2 && (in2->C != L.Cin2 || L.k != 1 || L.stride != 1)) return fail(h, -30, "conv " + L.name + ": bad fused pair");
-    const bool flat = (L.k == 1 && L.stride == 1 && (!in2 || L.stride2 == 1));
+    if (up && (res || post1)) return fail(h, -30, "conv " + L.name + ": up-residual excludes other epilogue inputs");
+    const bool flat = (L.k == 1 && L.stride == 1 && (!in2 || L.stride2 == 1) && !up);
     int tw, th, tiles_x, tiles_y, nimg;
     int rc;
     if (flat) {
@@ -362,8 +363,20 @@ int setup_conv(smapb_handle* h, const ConvLayer& L, const Act& in, const Act* re
     cp->n_tiles = L.Cout_pad / bn;
     cp->total_tiles = (int)(m_tiles * cp->n_tiles);
     cp->bias = L.bias_dev;
-    cp->has_res = res ? 1 : 0;
+    cp->has_res = (res || up) ? 1 : 0;
     cp->n_post = (post1 ? 1 : 0) + (post2 ? 1 : 0);
+    if (up) {  // fused bilinear x2 residual: the ring carries the low-resolution patch under each output tile
+        cp->up_mode = 1;
+        cp->up_Hi = up->H;
+        cp->up_Wi = up->W;
+        cp->up_pw = tw / 2 + 2;
+        cp->up_ph = th / 2 + 2;
+        if (up->H * 2 != Ho || up->W * 2 != Wo || up->C != L.Cout_pad || cp->up_pw * cp->up_ph > 128)
+            return fail(h, -30, "conv " + L.name + ": unsupported up-residual geometry");
+        rc = make_act_map(h, &cp->tmR[0], up->ptr, up->C, up->W, up->H, N, h->planes, up->plane(), cp->up_pw,
+                          cp->up_ph, 1, 32);
+        if (rc) return rc;
+    }
     if (post2 && !post1) return fail(h, -30, "conv " + L.name + ": post2 without post1");
     cp->out = out ? out->ptr : nullptr;
     cp->out_f32 = outf ? outf->ptr : nullptr;
@@ -382,7 +395,7 @@ int setup_conv(smapb_handle* h, const ConvLayer& L, const Act& in, const Act* re
     rc = make_w_map(h, &cp->tmB, L.w_dev, L.Cin + L.Cin2, L.Cout_pad, L.k * L.k, h->planes, bn);
     if (rc) return rc;
     // epilogue tiles: 32 channels x (tw x th) pixels of the output / residual planes
-    int n_in = 0;
+    int n_in = up ? 1 : 0;
     for (int which = 0; which < 4; which++) {
         const Act* t = which == 0 ? out : which == 1 ? res : which == 2 ? post1 : post2;
         if (!t) continue;
@@ -500,7 +513,7 @@ struct PlanBuilder {
         return &it->second;
     }
     Act conv(const std::string& name, const Act& in, int relu, const Act* res = nullptr, const Act* p1 = nullptr,
-             const Act* p2 = nullptr, const Act* in2 = nullptr) {
+             const Act* p2 = nullptr, const Act* in2 = nullptr, const Act* up = nullptr) {
         Act out;
         if (rc) return out;
         const ConvLayer* L = layer(name);
@@ -510,7 +523,7 @@ struct PlanBuilder {
         if (rc) return out;
         Op op;
         op.kind = OP_CONV;
-        rc = setup_conv(h, *L, in, res, p1, p2, &out, nullptr, relu, &op.cp, &op.block_n, &op.flops, in2);
+        rc = setup_conv(h, *L, in, res, p1, p2, &out, nullptr, relu, &op.cp, &op.block_n, &op.flops, in2, up);
         plan->ops.push_back(op);
         plan->n_conv++;
         plan->conv_flops += op.flops;
@@ -594,15 +607,11 @@ int build_plan(smapb_handle* h, int B, Plan** out_plan) {
             if (ind == 0) {
                 out = pb.conv(p + "u_skip", xin, 1);
             } else {
-                Act a = pb.conv(p + "u_skip", xin, 0);
-                Act tl = pb.conv(p + "up_conv", up_x, 0);  // 1x1 conv commuted in front of the bilinear x2
-                out = pb.new_act(a.N, a.H, a.W, a.C);
-                Op op;
-                op.kind = OP_UPADD;
-                op.a = a;
-                op.b = tl;
-                op.out = out;
-                plan->ops.push_back(op);
+                // out = relu(u_skip(x) + bilinear_x2(up_conv(up_x))): the 1x1 up_conv is commuted in front of the
+                // interpolation (both linear, bilinear weights sum to 1) and the interpolation + add + ReLU run in the
+                // u_skip epilogue
+                Act tl = pb.conv(p + "up_conv", up_x, 0);
+                out = pb.conv(p + "u_skip", xin, 1, nullptr, nullptr, nullptr, nullptr, &tl);
             }
             // heads: only those that reach the returned tensors (model/smap.py:418-419) are computed
             if (s == 2 && ind >= 1) {
