@@ -39,7 +39,7 @@ struct alignas(64) ConvParams {
     int tw_log2, th;  // tile: tw = 1 << tw_log2, tw * th == 128
     int tiles_x, tiles_y;
     int Cout;  // channel stride of the output / residual tensors (elements)
-    int ksize, stride, pad;
+    int kh, kw, stride, pad_y, pad_x;  // filter taps (kh x kw), spatial stride, zero padding
     int kchunks;  // Cin / 64
     int kchunks2, stride2;  // K-concatenated second 1x1 input: Cin2 / 64 (0 = none) and its spatial stride
     int n_tiles;  // Cout_pad / BLOCK_N
@@ -238,7 +238,7 @@ __global__ void __launch_bounds__(384, 1) conv_tc_kernel(const __grid_constant__
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int num_kb1 = p.ksize * p.ksize * p.kchunks;
+    const int num_kb1 = p.kh * p.kw * p.kchunks;
     const int num_kb = num_kb1 + p.kchunks2;
     const int tiles_per_img = p.tiles_x * p.tiles_y;
     const int tw = 1 << p.tw_log2;
@@ -254,15 +254,15 @@ __global__ void __launch_bounds__(384, 1) conv_tc_kernel(const __grid_constant__
                 const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
                 const int img = mt / tiles_per_img, r = mt - img * tiles_per_img;
                 const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
-                const int x_in0 = (tx << p.tw_log2) * p.stride - p.pad;
-                const int y_in0 = ty * p.th * p.stride - p.pad;
+                const int x_in0 = (tx << p.tw_log2) * p.stride - p.pad_x;
+                const int y_in0 = ty * p.th * p.stride - p.pad_y;
                 for (int kb = 0; kb < num_kb; kb++) {
                     mbar_wait(&empty_bar[stage], phase ^ 1u);
                     const uint32_t sbase = ring + stage * Cfg::STAGE_BYTES;
                     mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
                     if (kb < num_kb1) {
                         const int tap = kb / p.kchunks, kc = kb - tap * p.kchunks;
-                        const int ky = tap / p.ksize, kx = tap - ky * p.ksize;
+                        const int ky = tap / p.kw, kx = tap - ky * p.kw;
 #pragma unroll
                         for (int t = 0; t < Cfg::TA; t++) {
                             tma_load_5d(sbase + t * Cfg::A_BYTES, &p.tmA, &full_bar[stage], kc * 64, x_in0 + kx,

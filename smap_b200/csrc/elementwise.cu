@@ -140,6 +140,64 @@ cudaError_t launch_stem(const float* x, const float* wgt, const float* bias, int
 }
 
 // ---------------------------------------------------------------------------------------------
+// Space-to-depth of the network input for the tensor-core stem: fp32 NCHW [N,3,H,W] ->
+// split-bf16 [plane][N][H/2][W/2 + 3][16] with channel (by*2+bx)*3 + c = in[c][2y+by][2x+bx] (12 used, 4 zero) and
+// zero pixel columns 0,1 (left) and W/2+2 (right), so that every 4-pixel sliding window [x-2, x+1] of the 7x7/s2
+// receptive field is a contiguous, in-bounds 128-byte row for TMA.
+// ---------------------------------------------------------------------------------------------
+__global__ void s2d_kernel(const float* __restrict__ x, int N, int H, int W, __nv_bfloat16* __restrict__ out,
+                           long long plane_stride, int terms) {
+    const int H2 = H / 2, W2 = W / 2, WP = W2 + 3;
+    const long long total = (long long)N * H2 * WP;
+    pdl_wait();
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int xp = (int)(i % WP);
+        long long r = i / WP;
+        const int y2 = (int)(r % H2);
+        const int n = (int)(r / H2);
+        const int x2 = xp - 2;
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; j++) v[j] = 0.f;
+        if (x2 >= 0 && x2 < W2) {
+#pragma unroll
+            for (int c = 0; c < 3; c++)
+#pragma unroll
+                for (int by = 0; by < 2; by++) {
+                    const float2 p2 = *reinterpret_cast<const float2*>(x + (((size_t)n * 3 + c) * H + 2 * y2 + by) * W + 2 * x2);
+                    v[(by * 2 + 0) * 3 + c] = p2.x;
+                    v[(by * 2 + 1) * 3 + c] = p2.y;
+                }
+        }
+        uint32_t hw_[8], lw_[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            __nv_bfloat16 ah, al, bh, bl;
+            split_bf16(v[2 * j], ah, al);
+            split_bf16(v[2 * j + 1], bh, bl);
+            hw_[j] = pack_bf16x2(ah, bh);
+            lw_[j] = pack_bf16x2(al, bl);
+        }
+        uint4* oh = reinterpret_cast<uint4*>(out + i * 16);
+        oh[0] = make_uint4(hw_[0], hw_[1], hw_[2], hw_[3]);
+        oh[1] = make_uint4(hw_[4], hw_[5], hw_[6], hw_[7]);
+        if (terms == 2) {
+            uint4* ol = reinterpret_cast<uint4*>(out + plane_stride + i * 16);
+            ol[0] = make_uint4(lw_[0], lw_[1], lw_[2], lw_[3]);
+            ol[1] = make_uint4(lw_[4], lw_[5], lw_[6], lw_[7]);
+        }
+    }
+    pdl_trigger();
+}
+cudaError_t launch_s2d(const float* x, int N, int H, int W, __nv_bfloat16* out, long long plane_stride, int terms,
+                       cudaStream_t st) {
+    const long long total = (long long)N * (H / 2) * (W / 2 + 3);
+    const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+    s2d_kernel<<<blocks, 256, 0, st>>>(x, N, H, W, out, plane_stride, terms);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
 // helpers on 8-channel packets (uint4 = 8 bf16)
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void unpack8(const uint4& h, const uint4& l, float (&v)[8]) {

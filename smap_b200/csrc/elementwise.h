@@ -9,6 +9,8 @@ cudaError_t launch_f32_to_split(const float* x, __nv_bfloat16* out, long long n,
                                 cudaStream_t st);
 cudaError_t launch_stem(const float* x_nchw, const float* wgt, const float* bias, int N, int H, int W,
                         __nv_bfloat16* out, long long plane_stride, int terms, cudaStream_t st);
+cudaError_t launch_s2d(const float* x_nchw, int N, int H, int W, __nv_bfloat16* out, long long plane_stride, int terms,
+                       cudaStream_t st);
 cudaError_t launch_maxpool(const __nv_bfloat16* in, long long in_ps, int N, int H, int W, int C, __nv_bfloat16* out,
                            long long out_ps, int terms, cudaStream_t st);
 cudaError_t launch_upadd_relu(const __nv_bfloat16* a, long long a_ps, const __nv_bfloat16* t, long long t_ps, int N,

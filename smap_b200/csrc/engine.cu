@@ -70,11 +70,12 @@ struct ConvLayer {
     std::string name;
     int Cin = 0, Cout = 0, Cout_pad = 0, k = 1, stride = 1, pad = 0, relu = 0;
     int Cin2 = 0, stride2 = 1;  // K-concatenated second 1x1 input (weights hold Cin + Cin2 columns)
+    bool stem_s2d = false;      // space-to-depth stem: 4x1 taps over a sliding 4-pixel window view (see build_plan)
     __nv_bfloat16* w_dev = nullptr;  // [T][taps][Cout_pad][Cin]
     float* bias_dev = nullptr;       // [Cout_pad]
 };
 
-enum OpKind { OP_STEM, OP_MAXPOOL, OP_CONV, OP_UPADD, OP_HEADMERGE };
+enum OpKind { OP_STEM, OP_S2D, OP_MAXPOOL, OP_CONV, OP_UPADD, OP_HEADMERGE };
 struct Op {
     OpKind kind;
     // conv
@@ -109,6 +110,8 @@ struct smapb_handle {
     std::map<std::string, std::vector<int64_t>> raw_shape;
     std::map<std::string, ConvLayer> layers;
     float* stem_w = nullptr;  // [147][64]
+    ConvLayer stem_tc;        // space-to-depth tensor-core stem (4 ky-blocks x 64 k)
+    int stem_tc_ok = -1;      // -1 untested, 0 overlapped TMA view rejected (CUDA-core stem), 1 in use
     float* stem_b = nullptr;
     int nterms = 3;  // MMA terms (3 = bf16x3, 1 = bf16)
     int planes = 2;  // activation planes (2 or 1)
@@ -354,9 +357,11 @@ int setup_conv(smapb_handle* h, const ConvLayer& L, const Act& in, const Act* re
             }
     }
     cp->Cout = L.Cout_pad;
-    cp->ksize = L.k;
+    cp->kh = L.stem_s2d ? 4 : L.k;
+    cp->kw = L.stem_s2d ? 1 : L.k;
     cp->stride = L.stride;
-    cp->pad = L.pad;
+    cp->pad_y = L.stem_s2d ? 2 : L.pad;
+    cp->pad_x = L.stem_s2d ? 0 : L.pad;
     cp->kchunks = L.Cin / 64;
     cp->kchunks2 = L.Cin2 / 64;
     cp->stride2 = L.stride2;
@@ -408,6 +413,55 @@ int setup_conv(smapb_handle* h, const ConvLayer& L, const Act& in, const Act* re
     }
     *block_n_out = bn;
     if (flops_out) *flops_out = 2.0 * N * Ho * Wo * (double)L.Cout * (L.Cin * L.k * L.k + L.Cin2);
+    return 0;
+}
+
+// Tensor-core stem (7x7 s2 p3, 3 -> 64) as a 4x4 stride-1 convolution over the space-to-depth input: the A operand
+// of ky-block `ay` is, for every output pixel, the 128-byte window of 4 s2d pixels x 16 channels starting at padded
+// pixel ox - a *sliding* view whose dim-1 stride (32 B) is smaller than the dim-0 extent (128 B).
+int setup_stem_conv(smapb_handle* h, const __nv_bfloat16* s2d, long long s2d_plane, int N, int H2, int W2, const Act& out,
+                    ConvParams* cp, int* block_n_out, double* flops_out) {
+    const ConvLayer& L = h->stem_tc;
+    memset(cp, 0, sizeof(*cp));
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return fail(h, -20, "cuTensorMapEncodeTiled entry point not available");
+    double best = -1;
+    int tw = 16;
+    for (int c = 128; c >= 1; c >>= 1) {
+        const int t_h = 128 / c;
+        const double util = ((double)W2 * H2) / ((double)((W2 + c - 1) / c) * c * ((H2 + t_h - 1) / t_h) * t_h);
+        if (util > best + 1e-9) best = util, tw = c;
+    }
+    const int th = 128 / tw;
+    const long long WP = W2 + 3;
+    cuuint64_t dims[5] = {64, (cuuint64_t)W2, (cuuint64_t)H2, (cuuint64_t)N, (cuuint64_t)h->planes};
+    cuuint64_t strides[4] = {32, (cuuint64_t)WP * 32, (cuuint64_t)H2 * WP * 32, (cuuint64_t)s2d_plane * 2};
+    cuuint32_t box[5] = {64, (cuuint32_t)tw, (cuuint32_t)th, 1, 1};
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    CUresult r = fn(&cp->tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, (void*)s2d, dims, strides, box, es,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(h, -22, "sliding-window tensor map rejected: " + std::to_string((int)r));
+    int twl = 0;
+    while ((1 << twl) < tw) twl++;
+    cp->Hout = H2, cp->Wout = W2, cp->Nimg = N;
+    cp->tw_log2 = twl, cp->th = th;
+    cp->tiles_x = (W2 + tw - 1) / tw, cp->tiles_y = (H2 + th - 1) / th;
+    cp->Cout = 64;
+    cp->kh = 4, cp->kw = 1, cp->stride = 1, cp->pad_y = 2, cp->pad_x = 0;
+    cp->kchunks = 1;
+    cp->n_tiles = 1;
+    cp->total_tiles = cp->tiles_x * cp->tiles_y * N;
+    cp->bias = L.bias_dev;
+    cp->out = out.ptr;
+    cp->plane_stride = out.plane();
+    cp->relu = 1;
+    int rc = make_w_map(h, &cp->tmB, L.w_dev, 64, 64, 4, h->planes, 64);
+    if (rc) return rc;
+    rc = make_act_map(h, &cp->tmO, out.ptr, 64, W2, H2, N, h->planes, out.plane(), tw, th, 1, 32);
+    if (rc) return rc;
+    *block_n_out = 64;
+    *flops_out = 2.0 * N * H2 * W2 * 64.0 * 147.0;
     return 0;
 }
 
@@ -560,10 +614,42 @@ int build_plan(smapb_handle* h, int B, Plan** out_plan) {
     // stem + maxpool (model/smap.py:88-92)
     Act stem = pb.new_act(B, H / 2, W / 2, 64);
     {
-        Op op;
-        op.kind = OP_STEM;
-        op.out = stem;
-        plan->ops.push_back(op);
+        // tensor-core stem over the space-to-depth input when the driver accepts the sliding-window TMA view,
+        // otherwise the fp32 CUDA-core stem kernel (both are GPU paths; SMAPB_STEM=cuda forces the latter)
+        bool tc = h->stem_tc_ok != 0 && !(getenv("SMAPB_STEM") && !strcmp(getenv("SMAPB_STEM"), "cuda"));
+        if (tc) {
+            Act s2d;  // storage [plane][B][H/2][W/2+3][16]
+            s2d.N = B, s2d.H = H / 2, s2d.W = W / 2 + 3, s2d.C = 16;
+            void* p = nullptr;
+            if (cudaMalloc(&p, (size_t)s2d.plane() * 2 * h->planes) != cudaSuccess)
+                return fail(h, -10, "cudaMalloc failed for the s2d input");
+            plan->allocs.push_back(p);
+            s2d.ptr = (__nv_bfloat16*)p;
+            Op oc;
+            oc.kind = OP_CONV;
+            int rc2 = setup_stem_conv(h, s2d.ptr, s2d.plane(), B, H / 2, W / 2, stem, &oc.cp, &oc.block_n, &oc.flops);
+            if (rc2 == -22) {
+                h->stem_tc_ok = 0;
+                tc = false;
+            } else if (rc2) {
+                return rc2;
+            } else {
+                h->stem_tc_ok = 1;
+                Op os;
+                os.kind = OP_S2D;
+                os.out = s2d;
+                plan->ops.push_back(os);
+                plan->ops.push_back(oc);
+                plan->n_conv++;
+                plan->conv_flops += oc.flops;
+            }
+        }
+        if (!tc) {
+            Op op;
+            op.kind = OP_STEM;
+            op.out = stem;
+            plan->ops.push_back(op);
+        }
     }
     Act x = pb.new_act(B, H / 4, W / 4, 64);
     {
@@ -677,6 +763,10 @@ int run_plan(smapb_handle* h, Plan* plan, const float* imgs, float* hm2d, float*
                 CK(launch_stem(imgs, h->stem_w, h->stem_b, B, h->in_h, h->in_w, op.out.ptr, op.out.plane(), T, st));
                 prof_mark(h, PK_STEM, st, "stem7x7");
                 break;
+            case OP_S2D:
+                CK(launch_s2d(imgs, B, h->in_h, h->in_w, op.out.ptr, op.out.plane(), T, st));
+                prof_mark(h, PK_STEM, st, "s2d");
+                break;
             case OP_MAXPOOL:
                 CK(launch_maxpool(op.a.ptr, op.a.plane(), B, op.a.H, op.a.W, op.a.C, op.out.ptr, op.out.plane(), T, st));
                 prof_mark(h, PK_STEM, st, "maxpool");
@@ -685,7 +775,7 @@ int run_plan(smapb_handle* h, Plan* plan, const float* imgs, float* hm2d, float*
                 CK(launch_conv(op.cp, op.block_n, h->nterms, h->sm_count, st, h->use_pdl));
                 if (h->profiling) {
                     char d[160];
-                    snprintf(d, sizeof d, "conv k%d s%d cin%d cout%d out%dx%d bn%d tiles%d", op.cp.ksize, op.cp.stride,
+                    snprintf(d, sizeof d, "conv k%dx%d s%d cin%d cout%d out%dx%d bn%d tiles%d", op.cp.kh, op.cp.kw, op.cp.stride,
                              op.cp.kchunks * 64, op.cp.Cout, op.cp.Hout, op.cp.Wout, op.block_n, op.cp.total_tiles);
                     prof_mark(h, PK_CONV, st, d, op.flops);
                 }
@@ -787,6 +877,8 @@ void smapb_destroy(smapb_handle* h) {
         cudaFree(kv.second.w_dev);
         cudaFree(kv.second.bias_dev);
     }
+    cudaFree(h->stem_tc.w_dev);
+    cudaFree(h->stem_tc.bias_dev);
     void* ptrs[] = {h->peaks, h->scores, h->bodies, h->counts, h->imgs_dev, h->imgs_flip, h->hm, h->hm_flip, h->detd,
                     h->rootd, h->scratch_detd, h->scratch_rootd, h->scales_dev, h->records_dev, h->stem_w, h->stem_b};
     for (void* p : ptrs)
@@ -831,6 +923,10 @@ int smapb_finalize_weights(smapb_handle* h, int precision) {
             cudaFree(kv.second.bias_dev);
         }
         h->layers.clear();
+        cudaFree(h->stem_tc.w_dev);
+        cudaFree(h->stem_tc.bias_dev);
+        h->stem_tc.w_dev = nullptr;
+        h->stem_tc.bias_dev = nullptr;
     }
     h->nterms = precision;
     h->planes = new_planes;
@@ -867,6 +963,33 @@ int smapb_finalize_weights(smapb_handle* h, int precision) {
             }
             CK(cudaMemcpy(h->stem_w, w2.data(), w2.size() * 4, cudaMemcpyHostToDevice));
             CK(cudaMemcpy(h->stem_b, bf.data(), 64 * 4, cudaMemcpyHostToDevice));
+            {  // tensor-core stem weights: [plane][ay][co][k], k = ax*16 + (by*2+bx)*3 + c; ky = 2*ay+by-1, kx = 2*ax+bx-1
+                ConvLayer& S = h->stem_tc;
+                S.name = "top.conv(s2d)";
+                S.Cin = 64, S.Cout = 64, S.Cout_pad = 64, S.k = 1, S.stride = 1, S.pad = 0, S.stem_s2d = true;
+                const size_t plane = (size_t)4 * 64 * 64;
+                std::vector<uint16_t> host(plane * h->planes, 0);
+                for (int co = 0; co < 64; co++)
+                    for (int ay = 0; ay < 4; ay++)
+                        for (int ax = 0; ax < 4; ax++)
+                            for (int by = 0; by < 2; by++)
+                                for (int bx = 0; bx < 2; bx++)
+                                    for (int c = 0; c < 3; c++) {
+                                        const int ky = 2 * ay + by - 1, kx = 2 * ax + bx - 1;
+                                        if (ky < 0 || ky > 6 || kx < 0 || kx > 6) continue;
+                                        const float v = wf[((co * 3 + c) * 7 + ky) * 7 + kx];
+                                        const uint16_t hi = f32_to_bf16_rn(v);
+                                        const size_t o = ((size_t)ay * 64 + co) * 64 + ax * 16 + (by * 2 + bx) * 3 + c;
+                                        host[o] = hi;
+                                        if (h->planes == 2) host[plane + o] = f32_to_bf16_rn(v - bf16_to_f32(hi));
+                                    }
+                if (!S.w_dev) {
+                    if (dev_alloc(h, &S.w_dev, host.size())) return -10;
+                    if (dev_alloc(h, &S.bias_dev, 64)) return -10;
+                }
+                CK(cudaMemcpy(S.w_dev, host.data(), host.size() * 2, cudaMemcpyHostToDevice));
+                CK(cudaMemcpy(S.bias_dev, bf.data(), 64 * 4, cudaMemcpyHostToDevice));
+            }
             continue;
         }
         ConvLayer& L = h->layers[name];
