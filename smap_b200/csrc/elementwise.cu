@@ -389,6 +389,54 @@ cudaError_t launch_head_merge(const float* r4, const float* r3, const float* r2,
 }
 
 // ---------------------------------------------------------------------------------------------
+// Thin 3x3 heads (14- and 1-channel, model/smap.py:204-208) as tap expansion: a 1x1 GEMM produces
+// T[n,y,x,tap*C+c] = sum_ci w[c,ci,tap] a[n,y,x,ci] once per pixel (the 256-channel input is read once instead of
+// nine times), and this kernel gathers out[n,c,y,x] = bias[c] + sum_tap T[n, y+ky-1, x+kx-1, tap*C+c] straight into
+// the NCHW fp32 result.  CTA = 32 pixels of one row, smem transpose for coalesced NCHW stores.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+tapsum_kernel(const float* __restrict__ T, const float* __restrict__ bias, int N, int H, int W, int Cpad, int C,
+              float* __restrict__ out) {
+    __shared__ float tile[16][33];
+    const int x0 = blockIdx.x * 32, y = blockIdx.y, n = blockIdx.z;
+    pdl_wait();
+    for (int i = threadIdx.x; i < 32 * C; i += 256) {
+        const int px = i / C, c = i - px * C;
+        const int x = x0 + px;
+        float v = 0.f;
+        if (x < W) {
+            v = bias[c];
+#pragma unroll
+            for (int ky = 0; ky < 3; ky++) {
+                const int yy = y + ky - 1;
+                if (yy < 0 || yy >= H) continue;
+#pragma unroll
+                for (int kx = 0; kx < 3; kx++) {
+                    const int xx = x + kx - 1;
+                    if (xx < 0 || xx >= W) continue;
+                    v += T[(((size_t)n * H + yy) * W + xx) * Cpad + (ky * 3 + kx) * C + c];
+                }
+            }
+        }
+        tile[c][px] = v;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < C * 32; i += 256) {
+        const int c = i / 32, px = i - c * 32;
+        const int x = x0 + px;
+        if (x < W) out[(((size_t)n * C + c) * H + y) * W + x] = tile[c][px];
+    }
+    pdl_trigger();
+}
+cudaError_t launch_tapsum(const float* T, const float* bias, int N, int H, int W, int Cpad, int C, float* out,
+                          cudaStream_t st) {
+    if (C > 16) return cudaErrorInvalidValue;
+    dim3 grid((W + 31) / 32, H, N);
+    tapsum_kernel<<<grid, 256, 0, st>>>(T, bias, N, H, W, Cpad, C, out);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
 // Flip-TTA merge + per-image rescale, in place on hm [B,43,h,w] (exps/stage3_root2/test.py:55-70,111-112).
 // ---------------------------------------------------------------------------------------------
 __constant__ int c_flip_pair[43] = {0, 1, 2, 9, 10, 11, 12, 13, 14, 3, 4, 5, 6, 7, 8,

@@ -18,5 +18,7 @@ cudaError_t launch_upadd_relu(const __nv_bfloat16* a, long long a_ps, const __nv
                               cudaStream_t st);
 cudaError_t launch_head_merge(const float* r4, const float* r3, const float* r2, int N, int H, int W, int H3, int W3,
                               int H2, int W2, int Cpad, int Cout, float* out, cudaStream_t st);
+cudaError_t launch_tapsum(const float* T, const float* bias, int N, int H, int W, int Cpad, int C, float* out,
+                          cudaStream_t st);
 cudaError_t launch_merge_scale(float* hm, const float* hm_flip, int B, int h, int w, int do_scale, cudaStream_t st);
 }  // namespace smapb

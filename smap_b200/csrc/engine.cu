@@ -75,7 +75,7 @@ struct ConvLayer {
     float* bias_dev = nullptr;       // [Cout_pad]
 };
 
-enum OpKind { OP_STEM, OP_S2D, OP_MAXPOOL, OP_CONV, OP_UPADD, OP_HEADMERGE };
+enum OpKind { OP_STEM, OP_S2D, OP_MAXPOOL, OP_CONV, OP_UPADD, OP_HEADMERGE, OP_TAPSUM };
 struct Op {
     OpKind kind;
     // conv
@@ -87,6 +87,7 @@ struct Op {
     ActF32 f4, f3, f2;
     int cout = 0;  // head merge real channel count
     int which_out = 0;  // 0 hm2d, 1 detd, 2 rootd
+    const float* bias = nullptr;  // tap-sum bias
 };
 
 struct Plan {
@@ -134,6 +135,9 @@ struct smapb_handle {
     double* scales_dev = nullptr;
     smapb_record* records_dev = nullptr;
     bool use_pdl = getenv("SMAPB_PDL") != nullptr;  // programmatic dependent launch between conv kernels
+    cudaStream_t aux_stream = nullptr;  // second branch of the dual-stream forward
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    bool dual = getenv("SMAPB_DUAL") != nullptr;
     cudaStream_t own_stream = nullptr;  // blocking stream used when the caller passes the legacy default stream
     struct GraphEntry {
         int B, flip;
@@ -600,8 +604,9 @@ struct PlanBuilder {
     }
 };
 
-int build_plan(smapb_handle* h, int B, Plan** out_plan) {
-    auto it = h->plans.find(B);
+int build_plan(smapb_handle* h, int B, Plan** out_plan, int instance = 0) {
+    const int key = B + 100000 * instance;  // instance > 0: an independent copy (own activations) for a second stream
+    auto it = h->plans.find(key);
     if (it != h->plans.end()) {
         *out_plan = it->second.get();
         return 0;
@@ -661,6 +666,7 @@ int build_plan(smapb_handle* h, int B, Plan** out_plan) {
     }
     Act skip1[4], skip2[4];
     ActF32 res[4], resd3, resrd3;
+    std::string name_d, name_rd;
     for (int s = 0; s < 3 && !pb.rc; s++) {
         const std::string pre = "stage" + std::to_string(s) + ".";
         const bool gen_skip = s != 2;
@@ -706,9 +712,11 @@ int build_plan(smapb_handle* h, int B, Plan** out_plan) {
             }
             if (s == 2 && ind == 3) {
                 Act d1 = pb.conv(p + "res_d_conv1", out, 1);
-                resd3 = pb.conv_f32(p + "res_d_conv2", d1);
+                resd3 = pb.conv_f32(p + "res_d_conv2.tapexp", d1);
                 Act rd1 = pb.conv(p + "res_rd_conv1", out, 1);
-                resrd3 = pb.conv_f32(p + "res_rd_conv2", rd1);
+                resrd3 = pb.conv_f32(p + "res_rd_conv2.tapexp", rd1);
+                name_d = p + "res_d_conv2";
+                name_rd = p + "res_rd_conv2";
             }
             if (gen_skip) {
                 sk1[ind] = pb.conv(p + "skip1", xin, 1);
@@ -735,20 +743,22 @@ int build_plan(smapb_handle* h, int B, Plan** out_plan) {
         op.which_out = 0;
         plan->ops.push_back(op);
         Op od;
-        od.kind = OP_HEADMERGE;
+        od.kind = OP_TAPSUM;
         od.f4 = resd3;
         od.cout = 14;
         od.which_out = 1;
+        od.bias = h->layers[name_d].bias_dev;
         plan->ops.push_back(od);
         Op ord_;
-        ord_.kind = OP_HEADMERGE;
+        ord_.kind = OP_TAPSUM;
         ord_.f4 = resrd3;
         ord_.cout = 1;
         ord_.which_out = 2;
+        ord_.bias = h->layers[name_rd].bias_dev;
         plan->ops.push_back(ord_);
     }
     *out_plan = plan.get();
-    h->plans[B] = std::move(plan);
+    h->plans[key] = std::move(plan);
     return 0;
 }
 
@@ -785,6 +795,12 @@ int run_plan(smapb_handle* h, Plan* plan, const float* imgs, float* hm2d, float*
                                      op.a.C, op.out.ptr, op.out.plane(), T, st));
                 prof_mark(h, PK_ELEM, st, "upadd_relu");
                 break;
+            case OP_TAPSUM: {
+                float* dst = op.which_out == 1 ? detd : rootd;
+                CK(launch_tapsum(op.f4.ptr, op.bias, B, op.f4.H, op.f4.W, op.f4.C, op.cout, dst, st));
+                prof_mark(h, PK_ELEM, st, "tapsum");
+                break;
+            }
             case OP_HEADMERGE: {
                 float* dst = op.which_out == 0 ? hm2d : op.which_out == 1 ? detd : rootd;
                 CK(launch_head_merge(op.f4.ptr, op.f3.ptr, op.f2.ptr, B, op.f4.H, op.f4.W, op.f3.H, op.f3.W, op.f2.H,
@@ -857,6 +873,9 @@ int smapb_create(smapb_handle** out, int device, int max_batch, int in_h, int in
         return -10;
     }
     if (cudaStreamCreate(&h->own_stream) != cudaSuccess) h->own_stream = nullptr;
+    cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
     const char* aerr = nullptr;
     // association kernels stage whole planes in shared memory; larger maps are rejected at call time
     if (assoc_configure(h->h, h->w, &aerr) != 0) h->err = aerr ? aerr : "assoc_configure failed";
@@ -948,6 +967,8 @@ int smapb_finalize_weights(smapb_handle* h, int precision) {
         if (name.find(".downsample.layer") != std::string::npos &&
             (name.find(".0.conv_bn_relu3") != std::string::npos ||
              (name.size() > 13 && name.compare(name.size() - 13, 13, ".0.downsample") == 0)))
+            folded[name] = {wf, bf};
+        if (name.find("res_d_conv2") != std::string::npos || name.find("res_rd_conv2") != std::string::npos)
             folded[name] = {wf, bf};
         if (name == "top.conv") {
             if (Cin != 3 || Cout != 64 || k != 7) return fail(h, -40, "top.conv must be 3->64 7x7");
@@ -1048,6 +1069,26 @@ int smapb_finalize_weights(smapb_handle* h, int precision) {
         int rc3 = upload_conv_layer(h, F, wf, bf);
         if (rc3) return rc3;
     }
+    // thin 3x3 heads as tap expansion: rows (tap*C + c) of a 1x1 GEMM, bias applied by the gather kernel
+    for (auto& kv : folded) {
+        const std::string& nm = kv.first;
+        if (nm.find("res_d_conv2") == std::string::npos && nm.find("res_rd_conv2") == std::string::npos) continue;
+        const ConvLayer& L0 = h->layers[nm];
+        if (L0.k != 3) continue;
+        ConvLayer& E = h->layers[nm + ".tapexp"];
+        E.name = nm + ".tapexp";
+        E.Cin = L0.Cin;
+        E.Cout = 9 * L0.Cout;
+        E.Cout_pad = pad32(E.Cout);
+        E.k = 1, E.stride = 1, E.pad = 0;
+        std::vector<float> wf((size_t)E.Cout * E.Cin), bf(E.Cout, 0.f);
+        for (int c = 0; c < L0.Cout; c++)
+            for (int ci = 0; ci < L0.Cin; ci++)
+                for (int t = 0; t < 9; t++)
+                    wf[(size_t)(t * L0.Cout + c) * E.Cin + ci] = kv.second.first[((size_t)c * L0.Cin + ci) * 9 + t];
+        int rc4 = upload_conv_layer(h, E, wf, bf);
+        if (rc4) return rc4;
+    }
     if (!h->stem_w) return fail(h, -40, "top.conv weights missing");
     h->finalized = true;
     return 0;
@@ -1129,9 +1170,32 @@ __global__ void flip_w_kernel(const float* __restrict__ in, float* __restrict__ 
     }
 }
 
+// backbone forward of B frames; in dual mode as two half-batches on two streams (fork/join), so that the tail of
+// one half's kernel (partial last wave) overlaps the head of the other half's next kernel
+static int forward_maybe_dual(smapb_handle* h, Plan* plan, const float* imgs, int B, float* hm, float* detd, float* rootd,
+                              cudaStream_t st) {
+    if (!(h->dual && B >= 2 && B % 2 == 0 && !h->profiling)) return run_plan(h, plan, imgs, hm, detd, rootd, st);
+    const int Bh = B / 2;
+    Plan *pa = nullptr, *pb = nullptr;
+    int rc = build_plan(h, Bh, &pa, 1);
+    if (!rc) rc = build_plan(h, Bh, &pb, 2);
+    if (rc) return rc;
+    const size_t hw = (size_t)h->h * h->w;
+    CK(cudaEventRecord(h->ev_fork, st));
+    CK(cudaStreamWaitEvent(h->aux_stream, h->ev_fork, 0));
+    rc = run_plan(h, pa, imgs, hm, detd, rootd, st);
+    if (rc) return rc;
+    rc = run_plan(h, pb, imgs + (size_t)Bh * 3 * h->in_h * h->in_w, hm + (size_t)Bh * NC2D * hw, detd + (size_t)Bh * NL * hw,
+                  rootd + (size_t)Bh * hw, h->aux_stream);
+    if (rc) return rc;
+    CK(cudaEventRecord(h->ev_join, h->aux_stream));
+    CK(cudaStreamWaitEvent(st, h->ev_join, 0));
+    return 0;
+}
+
 static int infer_body(smapb_handle* h, Plan* plan, const float* imgs, const double* scales, int B, int do_flip,
                       smapb_record* records, cudaStream_t st) {
-    int rc = run_plan(h, plan, imgs, h->hm, h->detd, h->rootd, st);
+    int rc = forward_maybe_dual(h, plan, imgs, B, h->hm, h->detd, h->rootd, st);
     if (rc) return rc;
     const size_t hw = (size_t)h->h * h->w;
     if (do_flip) {
@@ -1146,7 +1210,7 @@ static int infer_body(smapb_handle* h, Plan* plan, const float* imgs, const doub
         CK(cudaGetLastError());
         prof_mark(h, PK_ELEM, st, "flip_w");
         h->launches++;
-        rc = run_plan(h, plan, h->imgs_flip, h->hm_flip, h->scratch_detd, h->scratch_rootd, st);
+        rc = forward_maybe_dual(h, plan, h->imgs_flip, B, h->hm_flip, h->scratch_detd, h->scratch_rootd, st);
         if (rc) return rc;
     }
     CK(launch_merge_scale(h->hm, do_flip ? h->hm_flip : nullptr, B, h->h, h->w, 1, st));
