@@ -57,6 +57,7 @@ struct alignas(64) ConvParams {
     // the ring carries the (ph x pw)-pixel patch under each output tile and the epilogue interpolates
     // (align_corners=True) before the ReLU.  up_mode = 0: plain residual.
     int up_mode, up_Hi, up_Wi, up_pw, up_ph;
+    long long* dbg;  // optional: per-role wait-cycle counters (tools/conv_micro.py --roles), null in production
 };
 
 // ---- tcgen05 / TMA PTX wrappers -----------------------------------------------------------------
@@ -158,11 +159,76 @@ __device__ __forceinline__ uint4 ldg_v4(const void* p) {
     return r;
 }
 
-template <int BLOCK_N, int NTERMS, bool RING>
+
+// ---- 2-CTA (cta_group::2) helpers -----------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `local_addr` in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA loads whose completion is signalled on an mbarrier given by shared::cluster address (the pair leader's barrier)
+__device__ __forceinline__ void tma_load_5d_cg2(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1,
+                                                int c2, int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, "
+        "%4, %5, %6, %7}], [%2];" ::"r"(dst),
+        "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_cg2(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1,
+                                                int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, "
+        "%4, %5, %6}], [%2];" ::"r"(dst),
+        "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tc_commit_cg2(uint64_t* bar) {  // arrive on the same barrier offset in both CTAs
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+            smem_u32(bar)),
+        "h"((uint16_t)3)
+        : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16_cg2(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+// mbar_wait that also returns the cycles spent waiting (role-level profiling; only used when p.dbg != null)
+__device__ __forceinline__ long long mbar_wait_timed(uint64_t* bar, uint32_t parity, bool timed) {
+    if (!timed) {
+        mbar_wait(bar, parity);
+        return 0;
+    }
+    const long long t0 = clock64();
+    mbar_wait(bar, parity);
+    return clock64() - t0;
+}
+
+template <int BLOCK_N, int NTERMS, bool RING, int CG = 1>
 struct ConvCfg {
     static constexpr int TA = (NTERMS == 3) ? 2 : 1;  // operand planes held per stage
     static constexpr int A_BYTES = 128 * 128;         // 128 rows x 64 bf16
-    static constexpr int B_BYTES = BLOCK_N * 128;
+    // CG = 2: a pair of CTAs (cta_group::2) computes a 256 x BLOCK_N tile; each CTA stages its own 128 rows of A and
+    // BLOCK_N/2 rows of B, and owns the 128 x BLOCK_N slice of the accumulator in its TMEM
+    static constexpr int B_BYTES = (BLOCK_N / CG) * 128;
     static constexpr int STAGE_BYTES = TA * (A_BYTES + B_BYTES);
     static constexpr int CHUNK_COLS = 32;              // epilogue granularity (one tcgen05.ld x32)
     static constexpr int CHUNKS = BLOCK_N / CHUNK_COLS;
@@ -183,9 +249,9 @@ struct ConvCfg {
     static_assert(BLOCK_N % 32 == 0 && BLOCK_N >= 32 && BLOCK_N <= 256, "BLOCK_N");
 };
 
-template <int BLOCK_N, int NTERMS, bool RING>
+template <int BLOCK_N, int NTERMS, bool RING, int CG = 1>
 __global__ void __launch_bounds__(384, 1) conv_tc_kernel(const __grid_constant__ ConvParams p) {
-    using Cfg = ConvCfg<BLOCK_N, NTERMS, RING>;
+    using Cfg = ConvCfg<BLOCK_N, NTERMS, RING, CG>;
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ unsigned char smem_raw[];
     // control block at the front, operand ring + epilogue staging 1024-aligned behind it
@@ -202,6 +268,7 @@ __global__ void __launch_bounds__(384, 1) conv_tc_kernel(const __grid_constant__
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;  // rank 0 = pair leader (issues the MMAs)
     const int n_extra = RING ? p.has_res + p.n_post : 0;  // epilogue input tensors streamed through the ring
     const bool tma_out = p.out != nullptr;
 
@@ -219,7 +286,7 @@ __global__ void __launch_bounds__(384, 1) conv_tc_kernel(const __grid_constant__
         }
         for (int a = 0; a < 2; a++) {
             mbar_init(&tfull_bar[a], 1);
-            mbar_init(&tempty_bar[a], 256);
+            mbar_init(&tempty_bar[a], 256 * CG);  // the leader's MMA waits for the epilogues of both CTAs
         }
         for (int s = 0; s < Cfg::RES_BUFS; s++) {
             mbar_init(&rfull_bar[s], 1);
@@ -228,13 +295,21 @@ __global__ void __launch_bounds__(384, 1) conv_tc_kernel(const __grid_constant__
         fence_mbar_init();
     }
     if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                     "n"(Cfg::TMEM_COLS)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (CG == 1) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                         "n"(Cfg::TMEM_COLS)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                         "n"(Cfg::TMEM_COLS)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
     __syncthreads();
+    if (CG == 2) cluster_sync_all();  // peer barriers are initialised before any remote arrive / TMA signal
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -243,41 +318,49 @@ __global__ void __launch_bounds__(384, 1) conv_tc_kernel(const __grid_constant__
     const int tiles_per_img = p.tiles_x * p.tiles_y;
     const int tw = 1 << p.tw_log2;
 
-    pdl_wait();  // inputs of this layer are produced by the previous kernel in the stream
+    pdl_wait();     // inputs of this layer are produced by the previous kernel in the stream
+    pdl_trigger();  // let the next kernel's CTAs be scheduled onto SMs as they drain (they block in their own wait)
 
     if (warp == 0) {
         // ============================ operand TMA producer ====================
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-                const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
+            long long w_empty = 0;
+            for (int tile = blockIdx.x / CG; tile < p.total_tiles; tile += gridDim.x / CG) {
+                const int nt = tile % p.n_tiles, mt = (tile / p.n_tiles) * CG + (int)cta_rank;
                 const int img = mt / tiles_per_img, r = mt - img * tiles_per_img;
                 const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
                 const int x_in0 = (tx << p.tw_log2) * p.stride - p.pad_x;
                 const int y_in0 = ty * p.th * p.stride - p.pad_y;
                 for (int kb = 0; kb < num_kb; kb++) {
-                    mbar_wait(&empty_bar[stage], phase ^ 1u);
+                    w_empty += mbar_wait_timed(&empty_bar[stage], phase ^ 1u, p.dbg != nullptr);
                     const uint32_t sbase = ring + stage * Cfg::STAGE_BYTES;
-                    mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+                    // CG = 2: both CTAs' loads complete on the LEADER's full barrier, which the leader arms for both
+                    if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES * CG);
+                    const uint32_t fbar = (CG == 2) ? mapa_u32(smem_u32(&full_bar[stage]), 0u) : 0u;
+                    const int brow = nt * BLOCK_N + (int)cta_rank * (BLOCK_N / CG);  // this CTA's rows of the weight tile
+                    int kcol, tapc, ax, ay;
+                    const CUtensorMap* amap;
                     if (kb < num_kb1) {
                         const int tap = kb / p.kchunks, kc = kb - tap * p.kchunks;
                         const int ky = tap / p.kw, kx = tap - ky * p.kw;
-#pragma unroll
-                        for (int t = 0; t < Cfg::TA; t++) {
-                            tma_load_5d(sbase + t * Cfg::A_BYTES, &p.tmA, &full_bar[stage], kc * 64, x_in0 + kx,
-                                        y_in0 + ky, img, t);
-                            tma_load_4d(sbase + Cfg::TA * Cfg::A_BYTES + t * Cfg::B_BYTES, &p.tmB, &full_bar[stage],
-                                        kc * 64, nt * BLOCK_N, tap, t);
-                        }
+                        amap = &p.tmA, kcol = kc * 64, tapc = tap, ax = x_in0 + kx, ay = y_in0 + ky;
                     } else {  // K-concatenated second input (1x1, own stride): weight columns continue after Cin
                         const int kc2 = kb - num_kb1;
+                        amap = &p.tmA2, kcol = kc2 * 64, tapc = 0;
+                        ax = (tx << p.tw_log2) * p.stride2, ay = ty * p.th * p.stride2;
+                    }
+                    const int wcol = (kb < num_kb1) ? kcol : (p.kchunks * 64 + kcol);
 #pragma unroll
-                        for (int t = 0; t < Cfg::TA; t++) {
-                            tma_load_5d(sbase + t * Cfg::A_BYTES, &p.tmA2, &full_bar[stage], kc2 * 64,
-                                        (tx << p.tw_log2) * p.stride2, ty * p.th * p.stride2, img, t);
-                            tma_load_4d(sbase + Cfg::TA * Cfg::A_BYTES + t * Cfg::B_BYTES, &p.tmB, &full_bar[stage],
-                                        (p.kchunks + kc2) * 64, nt * BLOCK_N, 0, t);
+                    for (int t = 0; t < Cfg::TA; t++) {
+                        const uint32_t da = sbase + t * Cfg::A_BYTES, db = sbase + Cfg::TA * Cfg::A_BYTES + t * Cfg::B_BYTES;
+                        if (CG == 1) {
+                            tma_load_5d(da, amap, &full_bar[stage], kcol, ax, ay, img, t);
+                            tma_load_4d(db, &p.tmB, &full_bar[stage], wcol, brow, tapc, t);
+                        } else {
+                            tma_load_5d_cg2(da, amap, fbar, kcol, ax, ay, img, t);
+                            tma_load_4d_cg2(db, &p.tmB, fbar, wcol, brow, tapc, t);
                         }
                     }
                     if (++stage == STAGES) {
@@ -286,23 +369,26 @@ __global__ void __launch_bounds__(384, 1) conv_tc_kernel(const __grid_constant__
                     }
                 }
             }
+            if (p.dbg) atomicAdd((unsigned long long*)&p.dbg[0], (unsigned long long)w_empty);
         }
     } else if (warp == 1) {
         // ============================ MMA issuer ==============================
-        if (lane == 0) {
-            // instruction descriptor: D=f32, A=B=bf16, both K-major, N, M=128
-            constexpr uint32_t idesc =
-                (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        if (lane == 0 && cta_rank == 0) {
+            // instruction descriptor: D=f32, A=B=bf16, both K-major, N, M = 128 (one CTA) or 256 (CTA pair)
+            constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) |
+                                       ((uint32_t)((128 * CG) >> 4) << 24);
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-                mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
+            long long w_full = 0, w_tempty = 0;
+            const long long t_begin = p.dbg ? clock64() : 0;
+            for (int tile = blockIdx.x / CG; tile < p.total_tiles; tile += gridDim.x / CG) {
+                w_tempty += mbar_wait_timed(&tempty_bar[acc], acc_phase ^ 1u, p.dbg != nullptr);
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BLOCK_N);
                 for (int kb = 0; kb < num_kb; kb++) {
-                    mbar_wait(&full_bar[stage], phase);
+                    w_full += mbar_wait_timed(&full_bar[stage], phase, p.dbg != nullptr);
                     tc_fence_after();
                     const uint32_t sbase = ring + stage * Cfg::STAGE_BYTES;
                     const uint64_t a0 = umma_desc_sw128(sbase);
@@ -311,23 +397,38 @@ __global__ void __launch_bounds__(384, 1) conv_tc_kernel(const __grid_constant__
 #pragma unroll
                     for (int k = 0; k < 4; k++) {  // 4 x UMMA_K(16) per 64-channel k-block; +32 B per step
                         const uint64_t ka = a0 + (uint64_t)(k * 2), kbd = b0 + (uint64_t)(k * 2);
-                        tc_mma_bf16(tmem_d, ka, kbd, idesc, (kb | k) != 0);  // a_hi * b_hi
-                        if (NTERMS == 3) {
-                            tc_mma_bf16(tmem_d, ka + A_STEP, kbd, idesc, 1u);  // a_lo * b_hi
-                            tc_mma_bf16(tmem_d, ka, kbd + B_STEP, idesc, 1u);  // a_hi * b_lo
+                        if (CG == 1) {
+                            tc_mma_bf16(tmem_d, ka, kbd, idesc, (kb | k) != 0);  // a_hi * b_hi
+                            if (NTERMS == 3) {
+                                tc_mma_bf16(tmem_d, ka + A_STEP, kbd, idesc, 1u);  // a_lo * b_hi
+                                tc_mma_bf16(tmem_d, ka, kbd + B_STEP, idesc, 1u);  // a_hi * b_lo
+                            }
+                        } else {
+                            tc_mma_bf16_cg2(tmem_d, ka, kbd, idesc, (kb | k) != 0);
+                            if (NTERMS == 3) {
+                                tc_mma_bf16_cg2(tmem_d, ka + A_STEP, kbd, idesc, 1u);
+                                tc_mma_bf16_cg2(tmem_d, ka, kbd + B_STEP, idesc, 1u);
+                            }
                         }
                     }
-                    tc_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+                    // frees the smem slot (in both CTAs of a pair) once these MMAs have read it
+                    if (CG == 1) tc_commit(&empty_bar[stage]); else tc_commit_cg2(&empty_bar[stage]);
                     if (++stage == STAGES) {
                         stage = 0;
                         phase ^= 1u;
                     }
                 }
-                tc_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+                if (CG == 1) tc_commit(&tfull_bar[acc]); else tc_commit_cg2(&tfull_bar[acc]);  // accumulator complete
                 if (++acc == 2) {
                     acc = 0;
                     acc_phase ^= 1u;
                 }
+            }
+            if (p.dbg) {
+                atomicAdd((unsigned long long*)&p.dbg[1], (unsigned long long)w_full);
+                atomicAdd((unsigned long long*)&p.dbg[2], (unsigned long long)w_tempty);
+                atomicAdd((unsigned long long*)&p.dbg[7], (unsigned long long)(clock64() - t_begin));
+                atomicAdd((unsigned long long*)&p.dbg[8], 1ull);
             }
         }
     } else if (warp == 3) {
@@ -338,8 +439,8 @@ __global__ void __launch_bounds__(384, 1) conv_tc_kernel(const __grid_constant__
             // mbarrier phase ahead of the fill it is waiting for.
             int cnt[2] = {0, 0};  // fills issued so far per group
             const int one = p.one_group;
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-                const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
+            for (int tile = blockIdx.x / CG; tile < p.total_tiles; tile += gridDim.x / CG) {
+                const int nt = tile % p.n_tiles, mt = (tile / p.n_tiles) * CG + (int)cta_rank;
                 const int img = mt / tiles_per_img, r = mt - img * tiles_per_img;
                 const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
                 for (int c = 0; c < Cfg::CHUNKS; c++) {
@@ -374,17 +475,18 @@ __global__ void __launch_bounds__(384, 1) conv_tc_kernel(const __grid_constant__
         int acc = 0;
         uint32_t acc_phase = 0;
         int rcnt = 0;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-            const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
+        long long w_tfull = 0, w_stage = 0;
+        for (int tile = blockIdx.x / CG; tile < p.total_tiles; tile += gridDim.x / CG) {
+            const int nt = tile % p.n_tiles, mt = (tile / p.n_tiles) * CG + (int)cta_rank;
             const int img = mt / tiles_per_img, r = mt - img * tiles_per_img;
             const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
             const int py = ty * p.th + (row >> p.tw_log2);
             const int px = (tx << p.tw_log2) + (row & (tw - 1));
-            const bool valid = (py < p.Hout) && (px < p.Wout);
+            const bool valid = (py < p.Hout) && (px < p.Wout) && (img < p.Nimg);
             const long long pix = ((long long)img * p.Hout + py) * p.Wout + px;
             const int n0 = nt * BLOCK_N;
 
-            mbar_wait(&tfull_bar[acc], acc_phase);
+            w_tfull += mbar_wait_timed(&tfull_bar[acc], acc_phase, p.dbg != nullptr && leader);
             tc_fence_after();
             const uint32_t taddr = tmem_base + (uint32_t)(acc * BLOCK_N) + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
@@ -481,7 +583,11 @@ __global__ void __launch_bounds__(384, 1) conv_tc_kernel(const __grid_constant__
                 const long long off = pix * p.Cout + n0 + c0;
                 if (tma_out) {
                     // this group's staging slot must have been drained by its previous TMA store
-                    if (leader) bulk_wait_read<0>();
+                    if (leader) {
+                        const long long t0 = p.dbg ? clock64() : 0;
+                        bulk_wait_read<0>();
+                        if (p.dbg) w_stage += clock64() - t0;
+                    }
                     epi_bar_sync(1 + g);
 #pragma unroll
                     for (int j = 0; j < 4; j++) {
@@ -515,22 +621,31 @@ __global__ void __launch_bounds__(384, 1) conv_tc_kernel(const __grid_constant__
                 }
             }
             tc_fence_before();
-            mbar_arrive(&tempty_bar[acc]);
+            if (CG == 1 || cta_rank == 0) mbar_arrive(&tempty_bar[acc]);
+            else mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[acc]), 0u));  // the pair leader's barrier
             if (++acc == 2) {
                 acc = 0;
                 acc_phase ^= 1u;
             }
         }
         if (leader && tma_out) bulk_wait_all();  // stores must be complete before the CTA retires
+        if (p.dbg && leader) {
+            atomicAdd((unsigned long long*)&p.dbg[3 + 2 * g], (unsigned long long)w_tfull);
+            atomicAdd((unsigned long long*)&p.dbg[4 + 2 * g], (unsigned long long)w_stage);
+        }
     }
 
-    pdl_trigger();
     tc_fence_before();
     __syncthreads();
+    if (CG == 2) cluster_sync_all();  // the leader's MMAs read this CTA's smem: nobody leaves before both are done
     if (warp == 2) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::TMEM_COLS)
-                     : "memory");
+        if (CG == 1)
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::TMEM_COLS)
+                         : "memory");
+        else
+            asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::TMEM_COLS)
+                         : "memory");
     }
 }
 

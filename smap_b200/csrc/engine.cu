@@ -6,6 +6,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <map>
 #include <memory>
 #include <string>
@@ -81,6 +82,7 @@ struct Op {
     // conv
     ConvParams cp;
     int block_n = 0;
+    int cg = 1;  // 2: CTA-pair (cta_group::2) tiles
     double flops = 0;
     // generic tensors
     Act a, b, out;
@@ -235,41 +237,59 @@ int make_w_map(smapb_handle* h, CUtensorMap* m, const __nv_bfloat16* ptr, int Ci
 // ------------------------------------------------------------------------------------------------
 // conv launch
 // ------------------------------------------------------------------------------------------------
-template <int BN, int NT, bool RING>
-cudaError_t launch_conv_inst2(const ConvParams& cp, int grid, cudaStream_t st, bool pdl) {
-    using Cfg = ConvCfg<BN, NT, RING>;
+template <int BN, int NT, bool RING, int CG>
+cudaError_t launch_conv_inst2(const ConvParams& cp, int sm_count, cudaStream_t st, bool pdl) {
+    using Cfg = ConvCfg<BN, NT, RING, CG>;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, NT, RING>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             Cfg::SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, NT, RING, CG>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
         if (e != cudaSuccess) return e;
         configured = true;
     }
+    const int slots = sm_count / CG;  // persistent CTAs (CG = 1) or CTA pairs (CG = 2)
+    const int units = cp.total_tiles < slots ? cp.total_tiles : slots;
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(grid);
+    cfg.gridDim = dim3(units * CG);
     cfg.blockDim = dim3(384);
     cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (CG == 2) {
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = 2;
+        attr[na].val.clusterDim.y = 1;
+        attr[na].val.clusterDim.z = 1;
+        na++;
+    }
+    if (pdl) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        na++;
+    }
     cfg.attrs = attr;
-    cfg.numAttrs = pdl ? 1 : 0;
-    return cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, NT, RING>, cp);
+    cfg.numAttrs = na;
+    return cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, NT, RING, CG>, cp);
 }
-template <int BN, int NT>
-cudaError_t launch_conv_inst(const ConvParams& cp, int grid, cudaStream_t st, bool pdl) {
-    return (cp.has_res + cp.n_post) ? launch_conv_inst2<BN, NT, true>(cp, grid, st, pdl)
-                                    : launch_conv_inst2<BN, NT, false>(cp, grid, st, pdl);
+template <int BN, int NT, int CG>
+cudaError_t launch_conv_inst(const ConvParams& cp, int sm_count, cudaStream_t st, bool pdl) {
+    return (cp.has_res + cp.n_post) ? launch_conv_inst2<BN, NT, true, CG>(cp, sm_count, st, pdl)
+                                    : launch_conv_inst2<BN, NT, false, CG>(cp, sm_count, st, pdl);
 }
-cudaError_t launch_conv(const ConvParams& cp, int block_n, int nterms, int sm_count, cudaStream_t st, bool pdl) {
-    const int grid = cp.total_tiles < sm_count ? cp.total_tiles : sm_count;
-#define SMAPB_CASE(BN)                                                              \
-    case BN:                                                                        \
-        return nterms == 3 ? launch_conv_inst<BN, 3>(cp, grid, st, pdl) : launch_conv_inst<BN, 1>(cp, grid, st, pdl);
+cudaError_t launch_conv(const ConvParams& cp, int block_n, int nterms, int sm_count, cudaStream_t st, bool pdl,
+                        int cg = 1) {
+    if (cg == 2) {  // CTA pairs: 256 x 256 tiles, bf16x3 only
+        if (block_n == 256 && nterms == 3) return launch_conv_inst<256, 3, 2>(cp, sm_count, st, pdl);
+        return cudaErrorInvalidValue;
+    }
+#define SMAPB_CASE(BN)                                                                  \
+    case BN:                                                                            \
+        return nterms == 3 ? launch_conv_inst<BN, 3, 1>(cp, sm_count, st, pdl)          \
+                           : launch_conv_inst<BN, 1, 1>(cp, sm_count, st, pdl);
     switch (block_n) {
         case 256:  // only the single-term mode has room for 256-wide operand stages next to the epilogue staging
-            return nterms == 1 ? launch_conv_inst<256, 1>(cp, grid, st, pdl) : cudaErrorInvalidValue;
+            return nterms == 1 ? launch_conv_inst<256, 1, 1>(cp, sm_count, st, pdl) : cudaErrorInvalidValue;
         SMAPB_CASE(128)
         SMAPB_CASE(64)
         SMAPB_CASE(32)
@@ -281,7 +301,7 @@ cudaError_t launch_conv(const ConvParams& cp, int block_n, int nterms, int sm_co
 // Fill a ConvParams for `layer` applied to `in`, producing (out | out_f32).
 int setup_conv(smapb_handle* h, const ConvLayer& L, const Act& in, const Act* res, const Act* post1, const Act* post2,
                const Act* out, const ActF32* outf, int relu, ConvParams* cp, int* block_n_out, double* flops_out,
-               const Act* in2 = nullptr, const Act* up = nullptr) {
+               const Act* in2 = nullptr, const Act* up = nullptr, int* cg_out = nullptr) {
     const int Ho = (in.H + 2 * L.pad - L.k) / L.stride + 1, Wo = (in.W + 2 * L.pad - L.k) / L.stride + 1;
     const int N = in.N;
     if (in.C != L.Cin) return fail(h, -30, "conv " + L.name + ": Cin mismatch");
@@ -339,27 +359,34 @@ int setup_conv(smapb_handle* h, const ConvLayer& L, const Act& in, const Act* re
     cp->tiles_x = tiles_x;
     cp->tiles_y = tiles_y;
     const long long m_tiles = (long long)tiles_x * tiles_y * nimg;
-    // BLOCK_N: the largest tile that still yields at least one full wave of CTAs, else the smallest >= 64
-    int bn = 0;
-    const int cands[4] = {256, 128, 64, 32};
-    // 256-wide tiles leave room for only single-buffered epilogue staging: keep them for long-K layers without
-    // a residual stream (compute-bound), use <= 128 elsewhere
-    const bool allow256 = (h->nterms == 1) && (res == nullptr) && ((L.Cin + L.Cin2) * L.k * L.k >= 512);
-    for (int c : cands) {
-        if (L.Cout_pad % c) continue;
-        if (c == 256 && !allow256) continue;
-        if (m_tiles * (L.Cout_pad / c) >= h->sm_count) {
-            bn = c;
-            break;
+    // Tile shape from a small cost model calibrated with per-role cycle counters on B200 (tools/conv_micro.py,
+    // SMAPB_ROLES=1): a k-block (64 channels, 12 MMAs) costs ~970 cycles at N=128 and ~880 at N=64 - both limited by
+    // the 128 B/clk shared-memory port, every MMA re-reads its A and B tiles - ~800 at N=32, and 1570 for a CTA pair
+    // (cta_group::2, 256 x 256: 4x the FLOPs, at the tensor-pipe rate); an epilogue chunk pair costs ~1750 cycles
+    // and overlaps the next tile's main loop.  time ~ waves x max(main loop, epilogue).
+    int bn = 0, cg = 1;
+    {
+        const int num_kb = L.k * L.k * (L.Cin / 64) + L.Cin2 / 64;
+        static const int pair_mode = getenv("SMAPB_PAIR") ? atoi(getenv("SMAPB_PAIR")) : 1;  // 0 never, 2 always
+        double best = 1e30;
+        const int cands[4] = {128, 64, 32, 256};
+        for (int c : cands) {
+            if (L.Cout_pad % c) continue;
+            const bool pair = (c == 256);
+            if (pair && !(pair_mode && cg_out && h->nterms == 3 && outf == nullptr)) continue;
+            if (c == 256 && h->nterms == 1) continue;
+            const double kb_cost = pair ? 1570.0 : c == 128 ? 970.0 : c == 64 ? 880.0 : 800.0;
+            const double epi = (c / 32) / 2.0 * 1750.0 + (c == 32 ? 875.0 : 0.0);
+            const long long units = (pair ? (m_tiles + 1) / 2 : m_tiles) * (L.Cout_pad / c);
+            const int slots = pair ? h->sm_count / 2 : h->sm_count;
+            const double waves = (double)((units + slots - 1) / slots);
+            double t = waves * std::max(num_kb * kb_cost, epi) + epi;  // + the last tile's exposed epilogue
+            if (pair && pair_mode == 2) t = 0;
+            if (t < best - 1e-9) best = t, bn = c, cg = pair ? 2 : 1;
         }
+        if (!bn) return fail(h, -30, "conv " + L.name + ": no tile shape for Cout_pad " + std::to_string(L.Cout_pad));
     }
-    if (!bn) {
-        for (int c : {64, 128, 256, 32})
-            if (L.Cout_pad % c == 0) {
-                bn = c;
-                break;
-            }
-    }
+    if (cg_out) *cg_out = cg;
     cp->Cout = L.Cout_pad;
     cp->kh = L.stem_s2d ? 4 : L.k;
     cp->kw = L.stem_s2d ? 1 : L.k;
@@ -370,7 +397,7 @@ int setup_conv(smapb_handle* h, const ConvLayer& L, const Act& in, const Act* re
     cp->kchunks2 = L.Cin2 / 64;
     cp->stride2 = L.stride2;
     cp->n_tiles = L.Cout_pad / bn;
-    cp->total_tiles = (int)(m_tiles * cp->n_tiles);
+    cp->total_tiles = (int)((cg == 2 ? (m_tiles + 1) / 2 : m_tiles) * cp->n_tiles);  // work units (tiles or pair tiles)
     cp->bias = L.bias_dev;
     cp->has_res = (res || up) ? 1 : 0;
     cp->n_post = (post1 ? 1 : 0) + (post2 ? 1 : 0);
@@ -401,7 +428,7 @@ int setup_conv(smapb_handle* h, const ConvLayer& L, const Act& in, const Act* re
                 cp->one_group = 1;
         }
     }
-    rc = make_w_map(h, &cp->tmB, L.w_dev, L.Cin + L.Cin2, L.Cout_pad, L.k * L.k, h->planes, bn);
+    rc = make_w_map(h, &cp->tmB, L.w_dev, L.Cin + L.Cin2, L.Cout_pad, L.k * L.k, h->planes, bn / cg);
     if (rc) return rc;
     // epilogue tiles: 32 channels x (tw x th) pixels of the output / residual planes
     int n_in = up ? 1 : 0;
@@ -581,7 +608,7 @@ struct PlanBuilder {
         if (rc) return out;
         Op op;
         op.kind = OP_CONV;
-        rc = setup_conv(h, *L, in, res, p1, p2, &out, nullptr, relu, &op.cp, &op.block_n, &op.flops, in2, up);
+        rc = setup_conv(h, *L, in, res, p1, p2, &out, nullptr, relu, &op.cp, &op.block_n, &op.flops, in2, up, &op.cg);
         plan->ops.push_back(op);
         plan->n_conv++;
         plan->conv_flops += op.flops;
@@ -782,11 +809,12 @@ int run_plan(smapb_handle* h, Plan* plan, const float* imgs, float* hm2d, float*
                 prof_mark(h, PK_STEM, st, "maxpool");
                 break;
             case OP_CONV:
-                CK(launch_conv(op.cp, op.block_n, h->nterms, h->sm_count, st, h->use_pdl));
+                CK(launch_conv(op.cp, op.block_n, h->nterms, h->sm_count, st, h->use_pdl, op.cg));
                 if (h->profiling) {
                     char d[160];
-                    snprintf(d, sizeof d, "conv k%dx%d s%d cin%d cout%d out%dx%d bn%d tiles%d", op.cp.kh, op.cp.kw, op.cp.stride,
-                             op.cp.kchunks * 64, op.cp.Cout, op.cp.Hout, op.cp.Wout, op.block_n, op.cp.total_tiles);
+                    snprintf(d, sizeof d, "conv k%dx%d s%d cin%d cout%d out%dx%d bn%d cg%d tiles%d", op.cp.kh, op.cp.kw,
+                             op.cp.stride, op.cp.kchunks * 64, op.cp.Cout, op.cp.Hout, op.cp.Wout, op.block_n, op.cg,
+                             op.cp.total_tiles);
                     prof_mark(h, PK_CONV, st, d, op.flops);
                 }
                 break;
@@ -1428,8 +1456,9 @@ int smapb_conv_test(smapb_handle* h, const float* x, const float* w, const float
     }
     ConvParams cp;
     int bn = 0;
+    int cg = 1;
     rc = setup_conv(h, L, in, res ? &r : nullptr, post1 ? &p1 : nullptr, post2 ? &p2 : nullptr, &out, nullptr, relu,
-                    &cp, &bn, nullptr);
+                    &cp, &bn, nullptr, nullptr, nullptr, &cg);
     if (rc) {
         cleanup();
         return rc;
@@ -1437,10 +1466,28 @@ int smapb_conv_test(smapb_handle* h, const float* x, const float* w, const float
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
-    CKT(launch_conv(cp, bn, h->nterms, h->sm_count, st, false));  // warm-up + result
+    long long* dbg_dev = nullptr;
+    if (getenv("SMAPB_ROLES")) {
+        CKT(cudaMalloc((void**)&dbg_dev, 16 * sizeof(long long)));
+        tmp.push_back(dbg_dev);
+        CKT(cudaMemset(dbg_dev, 0, 16 * sizeof(long long)));
+        cp.dbg = dbg_dev;
+    }
+    CKT(launch_conv(cp, bn, h->nterms, h->sm_count, st, false, cg));  // warm-up + result
+    if (dbg_dev) {
+        long long d[16];
+        CKT(cudaMemcpy(d, dbg_dev, sizeof d, cudaMemcpyDeviceToHost));
+        const double n = d[8] > 0 ? (double)d[8] : 1.0;  // number of MMA issuers (CTAs or pairs)
+        fprintf(stderr,
+                "[roles] bn%d cg%d units%d kb%d | mean cycles per issuer: total %.0f | producer wait-empty %.0f | mma "
+                "wait-full %.0f wait-tempty %.0f | epi g0 wait-tfull %.0f wait-stage %.0f | g1 wait-tfull %.0f wait-stage %.0f\n",
+                bn, cg, cp.total_tiles, cp.kh * cp.kw * cp.kchunks + cp.kchunks2, d[7] / n, d[0] / n / cg, d[1] / n,
+                d[2] / n, d[3] / n / cg, d[4] / n / cg, d[5] / n / cg, d[6] / n / cg);
+        cp.dbg = nullptr;
+    }
     const int reps = ms_out ? 5 : 0;
     cudaEventRecord(e0, st);
-    for (int i = 0; i < reps; i++) CKT(launch_conv(cp, bn, h->nterms, h->sm_count, st, false));
+    for (int i = 0; i < reps; i++) CKT(launch_conv(cp, bn, h->nterms, h->sm_count, st, false, cg));
     cudaEventRecord(e1, st);
     h->launches += 1 + reps;
     // de-pad + convert
