@@ -137,6 +137,8 @@ struct smapb_handle {
     double* scales_dev = nullptr;
     smapb_record* records_dev = nullptr;
     bool use_pdl = getenv("SMAPB_PDL") != nullptr;  // programmatic dependent launch between conv kernels
+    std::map<std::string, std::pair<int, int>> tune_cache;  // layer geometry -> measured best (BLOCK_N, CG)
+    bool autotune = getenv("SMAPB_NO_AUTOTUNE") == nullptr;
     cudaStream_t aux_stream = nullptr;  // second branch of the dual-stream forward
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     bool dual = getenv("SMAPB_DUAL") != nullptr;
@@ -301,7 +303,8 @@ cudaError_t launch_conv(const ConvParams& cp, int block_n, int nterms, int sm_co
 // Fill a ConvParams for `layer` applied to `in`, producing (out | out_f32).
 int setup_conv(smapb_handle* h, const ConvLayer& L, const Act& in, const Act* res, const Act* post1, const Act* post2,
                const Act* out, const ActF32* outf, int relu, ConvParams* cp, int* block_n_out, double* flops_out,
-               const Act* in2 = nullptr, const Act* up = nullptr, int* cg_out = nullptr) {
+               const Act* in2 = nullptr, const Act* up = nullptr, int* cg_out = nullptr, int force_bn = 0,
+               int force_cg = 0) {
     const int Ho = (in.H + 2 * L.pad - L.k) / L.stride + 1, Wo = (in.W + 2 * L.pad - L.k) / L.stride + 1;
     const int N = in.N;
     if (in.C != L.Cin) return fail(h, -30, "conv " + L.name + ": Cin mismatch");
@@ -376,15 +379,29 @@ int setup_conv(smapb_handle* h, const ConvLayer& L, const Act& in, const Act* re
             if (pair && !(pair_mode && cg_out && h->nterms == 3 && outf == nullptr)) continue;
             if (c == 256 && h->nterms == 1) continue;
             const double kb_cost = pair ? 1570.0 : c == 128 ? 970.0 : c == 64 ? 880.0 : 800.0;
-            const double epi = (c / 32) / 2.0 * 1750.0 + (c == 32 ? 875.0 : 0.0);
-            const long long units = (pair ? (m_tiles + 1) / 2 : m_tiles) * (L.Cout_pad / c);
+            const int n_extra = (res || up ? 1 : 0) + (post1 ? 1 : 0) + (post2 ? 1 : 0);
+            // epilogue: ~1750 cycles per chunk pair, more when it also consumes ring operands / interpolates
+            const double chunk_cost = 1750.0 + 600.0 * n_extra + (up ? 1500.0 : 0.0);
+            const double epi = (c / 32) / 2.0 * chunk_cost + (c == 32 ? 0.5 * chunk_cost : 0.0);
+            // HBM: this CTA's share is ~23 B/clk; per tile it writes 128 x c outputs, reads the ring operands and
+            // (once per m-tile, the other n-tiles hit L2) the A tile
+            const int n_tiles_c = L.Cout_pad / c;
+            const double mem = (128.0 * c * 4.0 * (1 + n_extra) + 32768.0 * num_kb / n_tiles_c) / 23.0;
+            const long long units = (pair ? (m_tiles + 1) / 2 : m_tiles) * n_tiles_c;
             const int slots = pair ? h->sm_count / 2 : h->sm_count;
             const double waves = (double)((units + slots - 1) / slots);
-            double t = waves * std::max(num_kb * kb_cost, epi) + epi;  // + the last tile's exposed epilogue
+            double t = waves * std::max(std::max(num_kb * kb_cost, epi), mem) + epi;  // + the last tile's exposed epilogue
+            t *= (c == 64 ? 1.05 : c == 32 ? 1.10 : 1.0);                             // near-ties go to the wider tile
             if (pair && pair_mode == 2) t = 0;
             if (t < best - 1e-9) best = t, bn = c, cg = pair ? 2 : 1;
         }
         if (!bn) return fail(h, -30, "conv " + L.name + ": no tile shape for Cout_pad " + std::to_string(L.Cout_pad));
+    }
+    if (force_bn) {  // autotuner override
+        bn = force_bn;
+        cg = force_cg ? force_cg : 1;
+        if (L.Cout_pad % bn || (cg == 2 && (bn != 256 || h->nterms != 3 || outf || !cg_out)) || (cg == 1 && bn == 256 && h->nterms == 3))
+            return fail(h, -31, "invalid forced tile");
     }
     if (cg_out) *cg_out = cg;
     cp->Cout = L.Cout_pad;
@@ -597,6 +614,57 @@ struct PlanBuilder {
         }
         return &it->second;
     }
+    // Empirical tile selection: time every valid (BLOCK_N, CG) for this layer geometry once (activation contents do not
+    // matter for the timing) and keep the fastest; the cost model only provides the starting point.
+    int tune(const ConvLayer& L, const Act& in, const Act* res, const Act* p1, const Act* p2, const Act* out, int relu,
+             const Act* in2, const Act* up, Op* op) {
+        char key[256];
+        snprintf(key, sizeof key, "%d/%d/%d k%d s%d %dx%dx%d r%d p%d u%d c2_%d s2_%d t%d", L.Cin, L.Cout_pad, L.Cin2, L.k,
+                 L.stride, in.N, in.H, in.W, res ? 1 : 0, (p1 ? 1 : 0) + (p2 ? 1 : 0), up ? 1 : 0, L.Cin2, L.stride2,
+                 h->nterms);
+        auto it = h->tune_cache.find(key);
+        int best_bn = 0, best_cg = 1;
+        if (it != h->tune_cache.end()) {
+            best_bn = it->second.first, best_cg = it->second.second;
+        } else {
+            cudaEvent_t e0, e1;
+            cudaEventCreate(&e0);
+            cudaEventCreate(&e1);
+            float best_ms = 1e30f;
+            const int cand[4][2] = {{128, 1}, {64, 1}, {256, 2}, {32, 1}};
+            for (auto& c : cand) {
+                if (L.Cout_pad % c[0]) continue;
+                if (c[1] == 2 && h->nterms != 3) continue;
+                if (c[0] == 32 && L.Cout_pad > 64) continue;
+                Op trial;
+                int rc2 = setup_conv(h, L, in, res, p1, p2, out, nullptr, relu, &trial.cp, &trial.block_n, &trial.flops, in2,
+                                     up, &trial.cg, c[0], c[1]);
+                if (rc2) continue;
+                float ms_best_c = 1e30f;
+                for (int rep = 0; rep < 4; rep++) {
+                    cudaEventRecord(e0, nullptr);
+                    if (launch_conv(trial.cp, trial.block_n, h->nterms, h->sm_count, nullptr, false, trial.cg) != cudaSuccess) {
+                        ms_best_c = 1e30f;
+                        break;
+                    }
+                    cudaEventRecord(e1, nullptr);
+                    if (cudaEventSynchronize(e1) != cudaSuccess) return fail(h, -10, "autotune launch failed");
+                    float ms = 0;
+                    cudaEventElapsedTime(&ms, e0, e1);
+                    if (rep > 0 && ms < ms_best_c) ms_best_c = ms;
+                }
+                if (ms_best_c < best_ms) best_ms = ms_best_c, best_bn = c[0], best_cg = c[1];
+            }
+            cudaEventDestroy(e0);
+            cudaEventDestroy(e1);
+            h->err.clear();
+            if (!best_bn) return 0;  // keep the model's choice
+            h->tune_cache[key] = {best_bn, best_cg};
+        }
+        if (best_bn == op->block_n && best_cg == op->cg) return 0;
+        return setup_conv(h, L, in, res, p1, p2, out, nullptr, relu, &op->cp, &op->block_n, &op->flops, in2, up, &op->cg,
+                          best_bn, best_cg);
+    }
     Act conv(const std::string& name, const Act& in, int relu, const Act* res = nullptr, const Act* p1 = nullptr,
              const Act* p2 = nullptr, const Act* in2 = nullptr, const Act* up = nullptr) {
         Act out;
@@ -609,6 +677,7 @@ struct PlanBuilder {
         Op op;
         op.kind = OP_CONV;
         rc = setup_conv(h, *L, in, res, p1, p2, &out, nullptr, relu, &op.cp, &op.block_n, &op.flops, in2, up, &op.cg);
+        if (!rc && h->autotune) rc = tune(*L, in, res, p1, p2, &out, relu, in2, up, &op);
         plan->ops.push_back(op);
         plan->n_conv++;
         plan->conv_flops += op.flops;
