@@ -90,6 +90,11 @@ struct Op {
     int cout = 0;  // head merge real channel count
     int which_out = 0;  // 0 hm2d, 1 detd, 2 rootd
     const float* bias = nullptr;  // tap-sum bias
+    // two-stream execution: side-branch ops (skip convs, heads) run on stream 1 and overlap the main chain
+    int stream = 0;
+    std::vector<int> waits;  // indices of producer ops on the OTHER stream this op must wait for
+    bool record = false;     // some op on the other stream consumes this op's output
+    cudaEvent_t ev = nullptr;
 };
 
 struct Plan {
@@ -99,6 +104,8 @@ struct Plan {
     int n_conv = 0;
     double conv_flops = 0;
     cudaGraphExec_t graph = nullptr;
+    std::map<const void*, int> producer;  // tensor -> index of the op that writes it (build time)
+    int last_side = -1;
 };
 
 }  // namespace
@@ -139,6 +146,7 @@ struct smapb_handle {
     bool use_pdl = getenv("SMAPB_PDL") != nullptr;  // programmatic dependent launch between conv kernels
     std::map<std::string, std::pair<int, int>> tune_cache;  // layer geometry -> measured best (BLOCK_N, CG)
     bool autotune = getenv("SMAPB_NO_AUTOTUNE") == nullptr;
+    bool two_streams = getenv("SMAPB_ONE_STREAM") == nullptr;  // side branches (heads, skip convs) on a second stream
     cudaStream_t aux_stream = nullptr;  // second branch of the dual-stream forward
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     bool dual = getenv("SMAPB_DUAL") != nullptr;
@@ -581,6 +589,26 @@ struct PlanBuilder {
     Plan* plan;
     int B;
     int rc = 0;
+    int cur_stream = 0;  // stream of the ops being added (0 main chain, 1 side branches)
+
+    // record op (just pushed) as the producer of `out_ptr` and wire cross-stream waits for its inputs
+    void wire(const void* out_ptr, std::initializer_list<const void*> inputs) {
+        const int idx = (int)plan->ops.size() - 1;
+        Op& op = plan->ops[idx];
+        op.stream = cur_stream;
+        for (const void* in : inputs) {
+            if (!in) continue;
+            auto it = plan->producer.find(in);
+            if (it == plan->producer.end()) continue;
+            Op& prod = plan->ops[it->second];
+            if (prod.stream != op.stream) {
+                prod.record = true;
+                op.waits.push_back(it->second);
+            }
+        }
+        if (out_ptr) plan->producer[out_ptr] = idx;
+        if (cur_stream == 1) plan->last_side = idx;
+    }
 
     Act new_act(int N, int H, int W, int C) {
         Act a;
@@ -679,6 +707,8 @@ struct PlanBuilder {
         rc = setup_conv(h, *L, in, res, p1, p2, &out, nullptr, relu, &op.cp, &op.block_n, &op.flops, in2, up, &op.cg);
         if (!rc && h->autotune) rc = tune(*L, in, res, p1, p2, &out, relu, in2, up, &op);
         plan->ops.push_back(op);
+        wire(out.ptr, {in.ptr, res ? res->ptr : nullptr, p1 ? p1->ptr : nullptr, p2 ? p2->ptr : nullptr,
+                       in2 ? in2->ptr : nullptr, up ? up->ptr : nullptr});
         plan->n_conv++;
         plan->conv_flops += op.flops;
         return out;
@@ -694,6 +724,7 @@ struct PlanBuilder {
         op.kind = OP_CONV;
         rc = setup_conv(h, *L, in, nullptr, nullptr, nullptr, nullptr, &out, 0, &op.cp, &op.block_n, &op.flops);
         plan->ops.push_back(op);
+        wire(out.ptr, {in.ptr});
         plan->n_conv++;
         plan->conv_flops += op.flops;
         return out;
@@ -740,7 +771,9 @@ int build_plan(smapb_handle* h, int B, Plan** out_plan, int instance = 0) {
                 os.kind = OP_S2D;
                 os.out = s2d;
                 plan->ops.push_back(os);
+                pb.wire(s2d.ptr, {});
                 plan->ops.push_back(oc);
+                pb.wire(stem.ptr, {s2d.ptr});
                 plan->n_conv++;
                 plan->conv_flops += oc.flops;
             }
@@ -750,6 +783,7 @@ int build_plan(smapb_handle* h, int B, Plan** out_plan, int instance = 0) {
             op.kind = OP_STEM;
             op.out = stem;
             plan->ops.push_back(op);
+            pb.wire(stem.ptr, {});
         }
     }
     Act x = pb.new_act(B, H / 4, W / 4, 64);
@@ -759,6 +793,7 @@ int build_plan(smapb_handle* h, int B, Plan** out_plan, int instance = 0) {
         op.a = stem;
         op.out = x;
         plan->ops.push_back(op);
+        pb.wire(x.ptr, {stem.ptr});
     }
     Act skip1[4], skip2[4];
     ActF32 res[4], resd3, resrd3;
@@ -801,6 +836,9 @@ int build_plan(smapb_handle* h, int B, Plan** out_plan, int instance = 0) {
                 Act tl = pb.conv(p + "up_conv", up_x, 0);
                 out = pb.conv(p + "u_skip", xin, 1, nullptr, nullptr, nullptr, nullptr, &tl);
             }
+            // Side branches (heads, skip convs) hang off `out` / `xin` and are only needed much later: they go to the
+            // second stream and overlap the main chain, filling SMs that small layers leave idle.
+            pb.cur_stream = h->two_streams ? 1 : 0;
             // heads: only those that reach the returned tensors (model/smap.py:418-419) are computed
             if (s == 2 && ind >= 1) {
                 Act r1 = pb.conv(p + "res_conv1", out, 1);
@@ -817,8 +855,10 @@ int build_plan(smapb_handle* h, int B, Plan** out_plan, int instance = 0) {
             if (gen_skip) {
                 sk1[ind] = pb.conv(p + "skip1", xin, 1);
                 sk2[ind] = pb.conv(p + "skip2", out, 1);
+                pb.cur_stream = 0;
                 if (ind == 3) cross = pb.conv(p + "cross_conv", out, 1);
             }
+            pb.cur_stream = 0;
             up_x = out;
         }
         for (int li = 0; li < 4; li++) {  // skip lists are finest-first (model/smap.py:281-282)
@@ -838,6 +878,7 @@ int build_plan(smapb_handle* h, int B, Plan** out_plan, int instance = 0) {
         op.cout = 43;
         op.which_out = 0;
         plan->ops.push_back(op);
+        pb.wire(nullptr, {res[3].ptr, res[2].ptr, res[1].ptr});
         Op od;
         od.kind = OP_TAPSUM;
         od.f4 = resd3;
@@ -845,6 +886,7 @@ int build_plan(smapb_handle* h, int B, Plan** out_plan, int instance = 0) {
         od.which_out = 1;
         od.bias = h->layers[name_d].bias_dev;
         plan->ops.push_back(od);
+        pb.wire(nullptr, {resd3.ptr});
         Op ord_;
         ord_.kind = OP_TAPSUM;
         ord_.f4 = resrd3;
@@ -852,7 +894,15 @@ int build_plan(smapb_handle* h, int B, Plan** out_plan, int instance = 0) {
         ord_.which_out = 2;
         ord_.bias = h->layers[name_rd].bias_dev;
         plan->ops.push_back(ord_);
+        pb.wire(nullptr, {resrd3.ptr});
+        // the main stream must not run ahead of the side stream into the next forward: the last op joins it
+        if (plan->last_side >= 0) {
+            plan->ops[plan->last_side].record = true;
+            plan->ops.back().waits.push_back(plan->last_side);
+        }
     }
+    for (Op& op : plan->ops)
+        if (op.record) cudaEventCreateWithFlags(&op.ev, cudaEventDisableTiming);
     *out_plan = plan.get();
     h->plans[key] = std::move(plan);
     return 0;
@@ -863,7 +913,14 @@ int run_plan(smapb_handle* h, Plan* plan, const float* imgs, float* hm2d, float*
     const int B = plan->B;
     const int T = h->planes;
     prof_mark(h, PK_START, st);
+    // profiling serialises everything on one stream (per-op event deltas); otherwise side-branch ops run on the
+    // handle's second stream, ordered against the main chain by events on exactly the tensors they exchange
+    const bool multi = !h->profiling && !h->dual && h->aux_stream != nullptr;
+    cudaStream_t const main_st = st;
     for (const Op& op : plan->ops) {
+        st = (multi && op.stream == 1) ? h->aux_stream : main_st;
+        if (multi)
+            for (int w : op.waits) CK(cudaStreamWaitEvent(st, plan->ops[w].ev, 0));
         switch (op.kind) {
             case OP_STEM:
                 CK(launch_stem(imgs, h->stem_w, h->stem_b, B, h->in_h, h->in_w, op.out.ptr, op.out.plane(), T, st));
@@ -907,6 +964,7 @@ int run_plan(smapb_handle* h, Plan* plan, const float* imgs, float* hm2d, float*
             }
         }
         h->launches++;
+        if (multi && op.record) CK(cudaEventRecord(op.ev, st));
         if (getenv("SMAPB_DEBUG_SYNC")) CK(cudaStreamSynchronize(st));
     }
     return 0;
@@ -986,6 +1044,8 @@ void smapb_destroy(smapb_handle* h) {
     for (auto& kv : h->plans) {
         if (kv.second->graph) cudaGraphExecDestroy(kv.second->graph);
         for (void* p : kv.second->allocs) cudaFree(p);
+        for (Op& op : kv.second->ops)
+            if (op.ev) cudaEventDestroy(op.ev);
     }
     for (auto& g : h->graphs) cudaGraphExecDestroy(g.exec);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
