@@ -343,6 +343,7 @@ int setup_conv(smapb_handle* h, const ConvLayer& L, const Act& in, const Act* re
         for (int c = 128; c >= 1; c >>= 1) {
             const int t_h = 128 / c;
             if (c * smax > 256 || t_h * smax > 256) continue;
+            if (up && (c / 2 + 2) * (t_h / 2 + 2) > 128) continue;  // the low-resolution patch must fit one ring slot
             const double util = ((double)Wo * Ho) / ((double)((Wo + c - 1) / c) * c * ((Ho + t_h - 1) / t_h) * t_h);
             if (util > best + 1e-9) {
                 best = util;

@@ -224,3 +224,10 @@ def test_lift_golden_cases(eng):
         assert np.array_equal(p2[0, :m].cpu().numpy(), g["c%d_pred2d" % ci])
         assert np.array_equal(rdp[0, :m].cpu().numpy(), g["c%d_rootdepth" % ci])
         np.testing.assert_allclose(p3[0, :m].cpu().numpy(), g["c%d_pred3d" % ci], rtol=1e-12, atol=1e-12)
+
+
+def test_config4_crowded_batch64(eng):
+    """BASELINE.json configs[3]: crowded synthetic scenes (15 persons/frame), a 64-frame batch in chunks of 8."""
+    for chunk in range(8):
+        hms, rd, _ = scenes(range(1000 + chunk * 8, 1008 + chunk * 8), persons=15)
+        check_connect(eng, hms, rd)

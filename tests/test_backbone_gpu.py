@@ -75,3 +75,22 @@ def test_backbone_832x512_vs_fp32_oracle():
     for a, b in zip(o1, out):
         assert rel(a[0], b[1]) < 1e-6
     eng.close()
+
+
+def test_backbone_1024x1024_config5():
+    """BASELINE.json configs[4]: backbone-only at 1024x1024 (the association is defined at 128x208 maps only)."""
+    from smap_b200.engine import Engine
+
+    sd = smap_torch.make_state_dict(0, "identity")
+    x = smap_torch.make_input(1, 1024, 1024, seed=2).cuda()
+    ref = smap_torch.smap_forward({k: v.cuda() for k, v in sd.items()}, x)
+    eng = Engine(0, max_batch=1, in_h=1024, in_w=1024)
+    eng.load_state_dict(sd)
+    out = eng.forward(x)
+    torch.cuda.synchronize()
+    for name, a, b in zip(("hm2d", "detd", "rootd"), out, ref):
+        assert a.shape == b.shape == (1, {"hm2d": 43, "detd": 14, "rootd": 1}[name], 256, 256)
+        assert rel(a, b) < TOL, (name, rel(a, b))
+    n_conv, flops = eng.plan_info(1)
+    assert abs(flops * 1e-9 - 740.0) / 740.0 < 0.06  # SURVEY 8(d): 740 GFLOP live graph (we commute the up_conv 1x1s)
+    eng.close()
