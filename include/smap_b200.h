@@ -104,6 +104,14 @@ int smapb_infer_device(smapb_handle* h, const float* imgs_nchw_dev, const double
 int smapb_infer_host(smapb_handle* h, const float* imgs_nchw_host, const double* scales_host, int B, int do_flip,
                      smapb_record* records_host, void* stream);
 
+/* Pipelined form of smapb_infer_host for streams of batches: two slots (0/1).  smapb_submit_host enqueues H2D (on a copy
+ * stream), the whole path and the D2H of the records for one batch and returns immediately; smapb_wait blocks until that
+ * slot's records are in `records_host`.  Submitting to slot s while slot 1-s computes overlaps the next batch's H2D with
+ * the current batch's compute.  Host buffers must stay valid (and should be pinned) until smapb_wait returns. */
+int smapb_submit_host(smapb_handle* h, int slot, const float* imgs_nchw_host, const double* scales_host, int B, int do_flip,
+                      smapb_record* records_host);
+int smapb_wait(smapb_handle* h, int slot);
+
 /* ---- introspection ----------------------------------------------------------------------------- */
 /* number of kernels launched by this handle since creation */
 int64_t smapb_launch_count(const smapb_handle* h);

@@ -13,7 +13,7 @@ EXPORTS = [
     "smapb_create", "smapb_destroy", "smapb_last_error", "smapb_version", "smapb_load_weight",
     "smapb_finalize_weights", "smapb_backbone_forward", "smapb_merge_scale", "smapb_assoc_extract",
     "smapb_assoc_connect", "smapb_lift3d", "smapb_infer_device", "smapb_infer_host", "smapb_launch_count",
-    "smapb_plan_info", "smapb_conv_test", "smapb_profile_begin", "smapb_profile_end",
+    "smapb_plan_info", "smapb_conv_test", "smapb_profile_begin", "smapb_profile_end", "smapb_submit_host", "smapb_wait",
 ]
 
 _lib = None
@@ -51,6 +51,8 @@ def load():
     lib.smapb_lift3d.argtypes = [vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp]
     lib.smapb_infer_device.argtypes = [vp, vp, vp, i32, i32, vp, vp]
     lib.smapb_infer_host.argtypes = [vp, vp, vp, i32, i32, vp, vp]
+    lib.smapb_submit_host.argtypes = [vp, i32, vp, vp, i32, i32, vp]
+    lib.smapb_wait.argtypes = [vp, i32]
     lib.smapb_launch_count.argtypes = [vp]
     lib.smapb_launch_count.restype = i64
     lib.smapb_profile_begin.argtypes = [vp]

@@ -144,6 +144,15 @@ struct smapb_handle {
     double* scales_dev = nullptr;
     smapb_record* records_dev = nullptr;
     bool use_pdl = getenv("SMAPB_PDL") != nullptr;  // programmatic dependent launch between conv kernels
+    // host-facing pipeline (smapb_submit_host / smapb_wait): two slots, H2D of slot s+1 overlaps the compute of slot s
+    struct Slot {
+        float* imgs = nullptr;
+        double* scales = nullptr;
+        smapb_record* records = nullptr;
+        cudaEvent_t h2d = nullptr, done = nullptr;
+        bool used = false;
+    } slots[2];
+    cudaStream_t copy_stream = nullptr;
     std::map<std::string, std::pair<int, int>> tune_cache;  // layer geometry -> measured best (BLOCK_N, CG)
     bool autotune = getenv("SMAPB_NO_AUTOTUNE") == nullptr;
     bool two_streams = getenv("SMAPB_ONE_STREAM") == nullptr;  // side branches (heads, skip convs) on a second stream
@@ -1049,6 +1058,14 @@ void smapb_destroy(smapb_handle* h) {
             if (op.ev) cudaEventDestroy(op.ev);
     }
     for (auto& g : h->graphs) cudaGraphExecDestroy(g.exec);
+    for (auto& S : h->slots) {
+        cudaFree(S.imgs);
+        cudaFree(S.scales);
+        cudaFree(S.records);
+        if (S.h2d) cudaEventDestroy(S.h2d);
+        if (S.done) cudaEventDestroy(S.done);
+    }
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     for (auto& kv : h->layers) {
         cudaFree(kv.second.w_dev);
@@ -1457,6 +1474,45 @@ int smapb_infer_host(smapb_handle* h, const float* imgs_host, const double* scal
     if (rc) return rc;
     CK(cudaMemcpyAsync(records_host, h->records_dev, (size_t)B * sizeof(smapb_record), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int smapb_submit_host(smapb_handle* h, int slot, const float* imgs_host, const double* scales_host, int B, int do_flip,
+                      smapb_record* records_host) {
+    if (!h) return -1;
+    if (slot < 0 || slot > 1) return fail(h, -1, "smapb_submit_host: slot must be 0 or 1");
+    if (B < 1 || B > h->max_batch) return fail(h, -1, "smapb_submit_host: B outside [1, max_batch]");
+    cudaSetDevice(h->device);
+    smapb_handle::Slot& S = h->slots[slot];
+    if (!S.imgs) {
+        const size_t MB = h->max_batch;
+        if (dev_alloc(h, &S.imgs, MB * 3 * h->in_h * h->in_w)) return -10;
+        if (dev_alloc(h, &S.scales, MB * SMAPB_SCALE_LEN)) return -10;
+        if (dev_alloc(h, &S.records, MB)) return -10;
+        CK(cudaEventCreateWithFlags(&S.h2d, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&S.done, cudaEventDisableTiming));
+        if (!h->copy_stream) CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    }
+    // the slot's buffers are free once its previous submission has completed
+    if (S.used) CK(cudaStreamWaitEvent(h->copy_stream, S.done, 0));
+    CK(cudaMemcpyAsync(S.imgs, imgs_host, (size_t)B * 3 * h->in_h * h->in_w * 4, cudaMemcpyHostToDevice, h->copy_stream));
+    CK(cudaMemcpyAsync(S.scales, scales_host, (size_t)B * SMAPB_SCALE_LEN * 8, cudaMemcpyHostToDevice, h->copy_stream));
+    CK(cudaEventRecord(S.h2d, h->copy_stream));
+    cudaStream_t st = h->own_stream;
+    CK(cudaStreamWaitEvent(st, S.h2d, 0));
+    int rc = smapb_infer_device(h, S.imgs, S.scales, B, do_flip, S.records, (void*)st);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(records_host, S.records, (size_t)B * sizeof(smapb_record), cudaMemcpyDeviceToHost, st));
+    CK(cudaEventRecord(S.done, st));
+    S.used = true;
+    return 0;
+}
+
+int smapb_wait(smapb_handle* h, int slot) {
+    if (!h) return -1;
+    if (slot < 0 || slot > 1 || !h->slots[slot].used) return fail(h, -1, "smapb_wait: nothing submitted on this slot");
+    cudaSetDevice(h->device);
+    CK(cudaEventSynchronize(h->slots[slot].done));
     return 0;
 }
 

@@ -150,6 +150,17 @@ class Engine:
                                               _ptr(out), _stream()), "smapb_infer_host")
         return out.numpy().view(RECORD_DTYPE).reshape(B)
 
+    def submit_host(self, slot, imgs, scales, out, do_flip=False):
+        """Pipelined infer_host: enqueue one batch on slot 0/1 and return immediately (see smapb_submit_host).
+        imgs: pinned CPU fp32 [B,3,H,W]; scales: pinned CPU float64 [B,9]; out: pinned CPU uint8 [B, RECORD_BYTES]."""
+        assert not imgs.is_cuda and imgs.dtype == torch.float32 and imgs.is_contiguous()
+        assert scales.dtype == torch.float64 and out.dtype == torch.uint8
+        self._check(self.lib.smapb_submit_host(self._h, slot, _ptr(imgs), _ptr(scales), imgs.shape[0], int(do_flip), _ptr(out)),
+                    "smapb_submit_host")
+
+    def wait(self, slot):
+        self._check(self.lib.smapb_wait(self._h, slot), "smapb_wait")
+
     # ---- introspection ------------------------------------------------------------------------
     def launch_count(self):
         return int(self.lib.smapb_launch_count(self._h))

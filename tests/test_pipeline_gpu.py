@@ -62,3 +62,22 @@ def test_infer_host_equals_infer_device(eng):
     b = records_to_numpy(eng.infer_device(x.cuda(), torch.from_numpy(scales).cuda()))
     assert a.tobytes() == b.tobytes()
     assert eng.launch_count() > 0
+
+
+def test_submit_wait_pipeline_equals_sync(eng):
+    """smapb_submit_host / smapb_wait (two-slot pipeline) returns the same records as the synchronous call."""
+    from smap_b200.engine import RECORD_BYTES, scale_row
+
+    sc = lift_numpy.default_scale(1920, 1080)
+    scales = torch.from_numpy(np.stack([scale_row(sc)] * 2)).pin_memory()
+    xs = [schema.make_input(2, 512, 832, seed=30 + i).pin_memory() for i in range(3)]
+    outs = [torch.zeros(2, RECORD_BYTES, dtype=torch.uint8).pin_memory() for _ in range(3)]
+    eng.submit_host(0, xs[0], scales, outs[0])
+    eng.submit_host(1, xs[1], scales, outs[1])
+    eng.wait(0)
+    eng.submit_host(0, xs[2], scales, outs[2])
+    eng.wait(1)
+    eng.wait(0)
+    for x, o in zip(xs, outs):
+        ref = eng.infer_host(x, scales)
+        assert o.numpy().tobytes() == ref.tobytes()
