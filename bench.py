@@ -48,6 +48,8 @@ def parse():
     ap.add_argument("--precision", default="bf16x3", choices=["bf16x3", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-csv", default="")
+    ap.add_argument("--ncu-one-step", action="store_true",
+                    help="bracket exactly one device-resident step with cudaProfilerStart/Stop and exit (for ncu --profile-from-start off)")
     return ap.parse_args()
 
 
@@ -218,6 +220,13 @@ def run_ours(args):
     for i in range(max(3, args.warmup)):
         step_device(i)
     torch.cuda.synchronize()
+    if args.ncu_one_step:
+        torch.cuda.profiler.start()
+        step_device(0)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        eng.close()
+        return
 
     sampler = ClockSampler(local)
     sampler.start()
@@ -254,6 +263,11 @@ def run_ours(args):
         conv_ms_per_step = conv_ms / prof_steps
         achieved = conv_flops * fwd / (conv_ms_per_step * 1e-3) * 1e-12 if conv_ms_per_step > 0 else 0.0
         total_prof_ms = sum(v[0] for v in prof.values()) / prof_steps
+        traffic, traffic_src = None, None
+        tp = os.path.join(ROOT, "profiles", "r01_conv_traffic.json")
+        if os.path.exists(tp):  # committed ncu capture of the same command (tools/gpu_profile.sh)
+            tj = json.load(open(tp))
+            traffic, traffic_src = tj["mean_dram_bytes_per_launch"], "profiles/r01_conv_traffic.json"
         line = {
             "metric": "end-to-end FPS @832x512 (backbone+association+lift)", "value": value, "unit": "frames/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_dev / args.steps,
@@ -274,7 +288,8 @@ def run_ours(args):
                          "algorithmic_gflop_per_step": conv_flops * fwd * 1e-9,
                          "tensor_pipe_flop_multiplier": 3 if args.precision == "bf16x3" else 1,
                          "kernel_ms_per_step": conv_ms_per_step, "share_of_step": conv_ms_per_step / total_prof_ms,
-                         "traffic": None},
+                         "traffic": traffic, "traffic_unit": "bytes per launch (dram read+write, ncu)",
+                         "traffic_source": traffic_src},
             "breakdown_ms_per_step": {k: v[0] / prof_steps for k, v in prof.items() if v[1]},
         }
         if not args.no_cpu_baseline:
