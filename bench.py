@@ -22,6 +22,7 @@ and /root/reference does not exist on the GPU box).
 """
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -47,6 +48,8 @@ def parse():
     ap.add_argument("--flip", type=int, default=0, help="flip-TTA (doubles the backbone work); BASELINE configs use 0")
     ap.add_argument("--precision", default="bf16x3", choices=["bf16x3", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--engines", type=int, default=int(os.environ.get("SMAPB_BENCH_ENGINES", "2")),
+                    help="handles per GPU: >1 keeps that many batches in flight on independent streams")
     ap.add_argument("--profile-csv", default="")
     ap.add_argument("--ncu-one-step", action="store_true",
                     help="bracket exactly one device-resident step with cudaProfilerStart/Stop and exit (for ncu --profile-from-start off)")
@@ -163,8 +166,14 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     B = args.batch
-    eng = Engine(local, max_batch=B, in_h=IN_H, in_w=IN_W)
-    eng.load_state_dict(schema.make_state_dict(0, "identity"), precision=args.precision)
+    sd0 = schema.make_state_dict(0, "identity")
+    engines = []
+    for _ in range(max(1, args.engines)):
+        e = Engine(local, max_batch=B, in_h=IN_H, in_w=IN_W)
+        e.load_state_dict(sd0, precision=args.precision)
+        engines.append(e)
+    eng = engines[0]
+    NE = len(engines)
     dev = torch.device("cuda", local)
 
     # inputs: NROT distinct batches so that consecutive steps never re-read the same frames from L2
@@ -178,24 +187,27 @@ def run_ours(args):
     host_out = torch.empty(B, RECORD_BYTES, dtype=torch.uint8).pin_memory()
 
     def step_device(i):
-        rec = eng.infer_device(dev_batches[i % NROT], scales_dev, do_flip=bool(args.flip))
+        rec = engines[i % NE].infer_device(dev_batches[i % NROT], scales_dev, do_flip=bool(args.flip))
         return sdist.allgather_records(rec)  # one NCCL all-gather of the skeleton records (no-op at world 1)
 
-    host_outs = [host_out, torch.empty(B, RECORD_BYTES, dtype=torch.uint8).pin_memory()]
+    DEPTH = 2 * NE  # batches in flight: two slots per handle
+    host_outs = [torch.empty(B, RECORD_BYTES, dtype=torch.uint8).pin_memory() for _ in range(DEPTH)]
 
-    def finish_host(slot):
-        eng.wait(slot)  # this step's records are in host memory
+    def finish_host(j):
+        engines[j % NE].wait((j // NE) % 2)  # step j's records are in host memory
         if world > 1:
-            sdist.allgather_records(host_outs[slot].to(dev, non_blocking=True))
+            sdist.allgather_records(host_outs[j % DEPTH].to(dev, non_blocking=True))
 
     def step_host(i, last=False):
-        # two-slot pipeline through the C ABI: the H2D of step i overlaps the compute of step i-1; every step still
-        # performs its own H2D (pinned frames) and D2H (records) inside the timed region
-        eng.submit_host(i % 2, host_batches[i % NROT], scales_host, host_outs[i % 2], do_flip=bool(args.flip))
-        if i > 0:
-            finish_host((i - 1) % 2)
+        # pipeline through the C ABI (two slots per handle): the H2D of step i overlaps the compute of earlier steps;
+        # every step still performs its own H2D (pinned frames) and D2H (records) inside the timed region
+        if i >= DEPTH:
+            finish_host(i - DEPTH)
+        engines[i % NE].submit_host((i // NE) % 2, host_batches[i % NROT], scales_host, host_outs[i % DEPTH],
+                                    do_flip=bool(args.flip))
         if last:
-            finish_host(i % 2)
+            for j in range(max(0, i - DEPTH + 1), i + 1):
+                finish_host(j)
 
     def timed(fn, steps):
         if world > 1:
@@ -217,7 +229,9 @@ def run_ours(args):
             dist.barrier()
         return ms, wall
 
-    for i in range(max(3, args.warmup)):
+    # every (handle, input batch) pair must have gone through its eager runs and graph capture before timing
+    n_warm = max(3, args.warmup, 3 * NE * NROT // math.gcd(NE, NROT) if NE > 1 else 3 * NROT)
+    for i in range(n_warm):
         step_device(i)
     torch.cuda.synchronize()
     if args.ncu_one_step:
@@ -230,14 +244,14 @@ def run_ours(args):
 
     sampler = ClockSampler(local)
     sampler.start()
-    l0 = eng.launch_count()
+    l0 = sum(e.launch_count() for e in engines)
     ms_dev, wall_dev = timed(step_device, args.steps)
-    launches = eng.launch_count() - l0
+    launches = sum(e.launch_count() for e in engines) - l0
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
-    for i in range(2):
-        step_host(i, last=(i == 1))
+    for i in range(DEPTH):
+        step_host(i, last=(i == DEPTH - 1))
 
     def run_host(i):
         step_host(i, last=(i == args.steps - 1))
@@ -270,14 +284,15 @@ def run_ours(args):
             traffic, traffic_src = tj["mean_dram_bytes_per_launch"], "profiles/r01_conv_traffic.json"
         line = {
             "metric": "end-to-end FPS @832x512 (backbone+association+lift)", "value": value, "unit": "frames/s",
-            "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_dev / args.steps,
+            "n_gpus": world, "steps": args.steps, "warmup": n_warm, "ms_per_step": ms_dev / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16x3 (split-bf16 operands, fp32 accumulate; fp32-faithful)" if args.precision == "bf16x3" else "bf16",
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "frames_per_gpu_per_step": B, "flip_tta": int(args.flip),
                        "l2": "inputs rotate over %d distinct batches (%.0f MB) and every step streams >2 GB of activations (> 126 MB L2)"
                              % (NROT, NROT * B * 3 * IN_H * IN_W * 4 / 1e6),
-                       "parallelism": "dp%d, one all-gather of skeleton records per step" % world},
+                       "parallelism": "dp%d, one all-gather of skeleton records per step" % world,
+                       "batches_in_flight_per_gpu": NE},
             "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": B * 3 * IN_H * IN_W * 4 + B * 9 * 8,
                     "d2h_bytes_per_step": B * RECORD_BYTES, "ms_per_step": 1e3 * wall_host / args.steps},
             "gpu_launches": int(launches),
@@ -301,7 +316,8 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-    eng.close()
+    for e in engines:
+        e.close()
 
 
 if __name__ == "__main__":

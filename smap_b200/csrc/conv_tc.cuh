@@ -505,7 +505,11 @@ __global__ void __launch_bounds__(384, 1) conv_tc_kernel(const __grid_constant__
                         hh[j] = lds_v4(rb + sw64_off(row, j));
                         ll[j] = (NTERMS == 3) ? lds_v4(rb + Cfg::CHUNK_BYTES + sw64_off(row, j)) : make_uint4(0, 0, 0, 0);
                     }
-                    mbar_arrive(&rempty_bar[rslot]);  // values are in registers: the slot can be refilled
+                    // The slot is refilled by TMA (async proxy) while these were generic-proxy reads: without a proxy
+                    // fence the refill is not ordered after loads that are still in flight, and under memory pressure it
+                    // did overtake them (one 16-byte unit of a row came back holding the NEXT chunk's residual).
+                    fence_proxy_async();
+                    mbar_arrive(&rempty_bar[rslot]);
                 };
                 auto add_planes = [&](float(&vv)[32], const uint4(&hh)[4], const uint4(&ll)[4]) {
 #pragma unroll
@@ -555,6 +559,7 @@ __global__ void __launch_bounds__(384, 1) conv_tc_kernel(const __grid_constant__
                         for (int e = 0; e < 8; e++)
                             upv[8 * j + e] = hy0 * (wx0 * q[0][e] + wx1 * q[1][e]) + hy1 * (wx0 * q[2][e] + wx1 * q[3][e]);
                     }
+                    fence_proxy_async();  // generic reads of the slot before its async-proxy (TMA) refill, as above
                     mbar_arrive(&rempty_bar[rslot]);
                 }
                 tmem_ld_wait();

@@ -415,6 +415,11 @@ int setup_conv(smapb_handle* h, const ConvLayer& L, const Act& in, const Act* re
         }
         if (!bn) return fail(h, -30, "conv " + L.name + ": no tile shape for Cout_pad " + std::to_string(L.Cout_pad));
     }
+    if (!force_bn && getenv("SMAPB_FORCE_TILE")) {  // debug: "bn,cg" for every layer where it is valid
+        int fb = 0, fc = 1;
+        if (sscanf(getenv("SMAPB_FORCE_TILE"), "%d,%d", &fb, &fc) >= 1 && L.Cout_pad % fb == 0 && !(fc == 2 && (outf || !cg_out)))
+            force_bn = fb, force_cg = fc;
+    }
     if (force_bn) {  // autotuner override
         bn = force_bn;
         cg = force_cg ? force_cg : 1;
@@ -819,9 +824,12 @@ int build_plan(smapb_handle* h, int B, Plan** out_plan, int instance = 0) {
                 Act o1 = pb.conv(p + "conv_bn_relu1", t, 1);
                 Act o2 = pb.conv(p + "conv_bn_relu2", o1, 1);
                 const bool last = (b == LAYERS[li] - 1) && s > 0;
-                if (b == 0) {
+                if (b == 0 && !getenv("SMAPB_NO_FUSE_DS")) {
                     // relu(conv3(o2) + downsample(x)) as one K-concatenated GEMM
                     t = pb.conv(p + "fused_conv3_downsample", o2, 1, nullptr, nullptr, nullptr, &t);
+                } else if (b == 0) {  // debug: separate downsample + residual
+                    Act idn = pb.conv(p + "downsample", t, 0);
+                    t = pb.conv(p + "conv_bn_relu3", o2, 1, &idn);
                 } else {
                     // out = relu(conv3 + x) [ + skip1 + skip2 ]   (model/smap.py:74-75,143)
                     t = pb.conv(p + "conv_bn_relu3", o2, 1, &t, last ? &skip1[li] : nullptr,
@@ -844,7 +852,19 @@ int build_plan(smapb_handle* h, int B, Plan** out_plan, int instance = 0) {
                 // interpolation (both linear, bilinear weights sum to 1) and the interpolation + add + ReLU run in the
                 // u_skip epilogue
                 Act tl = pb.conv(p + "up_conv", up_x, 0);
-                out = pb.conv(p + "u_skip", xin, 1, nullptr, nullptr, nullptr, nullptr, &tl);
+                if (!getenv("SMAPB_NO_FUSE_UP")) {
+                    out = pb.conv(p + "u_skip", xin, 1, nullptr, nullptr, nullptr, nullptr, &tl);
+                } else {  // debug: separate bilinear + add + relu kernel
+                    Act a = pb.conv(p + "u_skip", xin, 0);
+                    out = pb.new_act(a.N, a.H, a.W, a.C);
+                    Op op;
+                    op.kind = OP_UPADD;
+                    op.a = a;
+                    op.b = tl;
+                    op.out = out;
+                    plan->ops.push_back(op);
+                    pb.wire(out.ptr, {a.ptr, tl.ptr});
+                }
             }
             // Side branches (heads, skip convs) hang off `out` / `xin` and are only needed much later: they go to the
             // second stream and overlap the main chain, filling SMs that small layers leave idle.
@@ -927,7 +947,10 @@ int run_plan(smapb_handle* h, Plan* plan, const float* imgs, float* hm2d, float*
     // handle's second stream, ordered against the main chain by events on exactly the tensors they exchange
     const bool multi = !h->profiling && !h->dual && h->aux_stream != nullptr;
     cudaStream_t const main_st = st;
+    const int stop_after = getenv("SMAPB_DEBUG_STOP") ? atoi(getenv("SMAPB_DEBUG_STOP")) : 1 << 30;
+    int op_idx = 0;
     for (const Op& op : plan->ops) {
+        if (op_idx++ >= stop_after) break;
         st = (multi && op.stream == 1) ? h->aux_stream : main_st;
         if (multi)
             for (int w : op.waits) CK(cudaStreamWaitEvent(st, plan->ops[w].ev, 0));
@@ -1278,7 +1301,9 @@ int smapb_backbone_forward(smapb_handle* h, const float* imgs, int B, float* hm2
     Plan* plan = nullptr;
     int rc = build_plan(h, B, &plan);
     if (rc) return rc;
-    return run_plan(h, plan, imgs, hm2d, detd, rootd, (cudaStream_t)stream);
+    // NULL = legacy default stream: run on the handle's own blocking stream (ordered with the caller's default-stream
+    // work by legacy-stream semantics, but concurrent with other handles)
+    return run_plan(h, plan, imgs, hm2d, detd, rootd, stream ? (cudaStream_t)stream : h->own_stream);
 }
 
 int smapb_merge_scale(smapb_handle* h, float* hm2d, const float* hm2d_flip, int B, int do_scale, void* stream) {
@@ -1514,6 +1539,81 @@ int smapb_wait(smapb_handle* h, int slot) {
     cudaSetDevice(h->device);
     CK(cudaEventSynchronize(h->slots[slot].done));
     return 0;
+}
+
+// debug: 64-bit checksums of every plan op's output tensor after the last forward (tools/debug_ops.py)
+__global__ void checksum_kernel(const uint32_t* __restrict__ p, long long nwords, unsigned long long* out) {
+    unsigned long long acc = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += (long long)gridDim.x * blockDim.x)
+        acc += (unsigned long long)p[i] * (unsigned long long)((i % 1021) + 1);
+    atomicAdd(out, acc);
+}
+// debug: raw copy of plan op `idx`'s split output (both planes, bf16 bits) to host; returns bytes copied
+long long smapb_debug_dump(smapb_handle* h, int B, int idx, void* host, long long max_bytes, int which) {
+    if (!h) return -1;
+    cudaSetDevice(h->device);
+    Plan* plan = nullptr;
+    int rc = build_plan(h, B, &plan);
+    if (rc) return rc;
+    cudaDeviceSynchronize();
+    int n = 0;
+    for (const Op& op : plan->ops) {
+        const void* ptr = nullptr;
+        long long bytes = 0;
+        if (op.kind == OP_CONV && op.cp.out) ptr = op.cp.out, bytes = op.cp.plane_stride * h->planes * 2;
+        else if (op.kind == OP_CONV && op.cp.out_f32) ptr = op.cp.out_f32, bytes = op.cp.plane_stride * 4;
+        else if (op.out.ptr) ptr = op.out.ptr, bytes = op.out.plane() * h->planes * 2;
+        else continue;
+        if (n++ != idx) continue;
+        (void)which;
+        if (bytes > max_bytes) bytes = max_bytes;
+        if (bytes > 0) cudaMemcpy(host, ptr, (size_t)bytes, cudaMemcpyDeviceToHost);
+        return bytes;
+    }
+    return -2;
+}
+
+int smapb_debug_checksums(smapb_handle* h, int B, unsigned long long* sums, int max_ops, char* desc, int desc_stride) {
+    if (!h) return -1;
+    cudaSetDevice(h->device);
+    Plan* plan = nullptr;
+    int rc = build_plan(h, B, &plan);
+    if (rc) return rc;
+    CK(cudaDeviceSynchronize());
+    unsigned long long* d = nullptr;
+    CK(cudaMalloc((void**)&d, 8));
+    int n = 0;
+    for (const Op& op : plan->ops) {
+        if (n >= max_ops) break;
+        const void* ptr = nullptr;
+        long long words = 0;
+        char buf[160];
+        if (op.kind == OP_CONV && op.cp.out) {
+            ptr = op.cp.out;
+            words = op.cp.plane_stride * h->planes / 2;
+            snprintf(buf, sizeof buf, "conv k%dx%d s%d cin%d(+%d) cout%d out%dx%d bn%d cg%d res%d post%d up%d", op.cp.kh, op.cp.kw,
+                     op.cp.stride, op.cp.kchunks * 64, op.cp.kchunks2 * 64, op.cp.Cout, op.cp.Hout, op.cp.Wout, op.block_n,
+                     op.cg, op.cp.has_res, op.cp.n_post, op.cp.up_mode);
+        } else if (op.kind == OP_CONV && op.cp.out_f32) {
+            ptr = op.cp.out_f32;
+            words = op.cp.plane_stride;
+            snprintf(buf, sizeof buf, "conv_f32 k%dx%d cin%d cout%d out%dx%d bn%d", op.cp.kh, op.cp.kw, op.cp.kchunks * 64,
+                     op.cp.Cout, op.cp.Hout, op.cp.Wout, op.block_n);
+        } else if (op.out.ptr) {
+            ptr = op.out.ptr;
+            words = op.out.plane() * h->planes / 2;
+            snprintf(buf, sizeof buf, "op kind %d out %dx%dx%d", (int)op.kind, op.out.H, op.out.W, op.out.C);
+        } else {
+            continue;
+        }
+        CK(cudaMemset(d, 0, 8));
+        checksum_kernel<<<148 * 4, 256>>>((const uint32_t*)ptr, words, d);
+        CK(cudaMemcpy(&sums[n], d, 8, cudaMemcpyDeviceToHost));
+        if (desc) snprintf(desc + (size_t)n * desc_stride, desc_stride, "%s", buf);
+        n++;
+    }
+    cudaFree(d);
+    return n;
 }
 
 int64_t smapb_launch_count(const smapb_handle* h) { return h ? h->launches : 0; }

@@ -203,3 +203,41 @@ class Engine:
 def records_to_numpy(rec):
     """uint8 cuda/cpu tensor [B, RECORD_BYTES] -> numpy structured array [B]."""
     return rec.cpu().numpy().view(RECORD_DTYPE).reshape(rec.shape[0])
+
+
+class EnginePool:
+    """N independent handles on one GPU (each with its own workspace, plan and streams), used round-robin so that N
+    batches are in flight: the tail of one batch's kernels (partial last waves) overlaps the other batch's kernels and
+    the H2D of the next batch overlaps compute.  Two handles give +6 % throughput on B200 (bench.py --engines)."""
+
+    def __init__(self, n=2, device=0, max_batch=8, in_h=512, in_w=832):
+        self.engines = [Engine(device, max_batch, in_h, in_w) for _ in range(n)]
+        self._next = 0
+        self._tickets = {}
+
+    def load_state_dict(self, sd, precision="bf16x3"):
+        for e in self.engines:
+            e.load_state_dict(sd, precision)
+
+    def submit(self, imgs, scales, out, do_flip=False):
+        """Enqueue one host batch (pinned tensors, see Engine.submit_host); returns a ticket for result()."""
+        t = self._next
+        self._next += 1
+        n = len(self.engines)
+        e, slot = self.engines[t % n], (t // n) % 2
+        prev = t - 2 * n
+        if prev in self._tickets:  # the slot is about to be reused: its previous occupant must be collected first
+            self.result(prev)
+        e.submit_host(slot, imgs, scales, out, do_flip)
+        self._tickets[t] = (e, slot, out)
+        return t
+
+    def result(self, ticket):
+        """Block until the batch is done; returns its records as a numpy structured array."""
+        e, slot, out = self._tickets.pop(ticket)
+        e.wait(slot)
+        return out.numpy().view(RECORD_DTYPE).reshape(out.shape[0])
+
+    def close(self):
+        for e in self.engines:
+            e.close()

@@ -81,3 +81,27 @@ def test_submit_wait_pipeline_equals_sync(eng):
     for x, o in zip(xs, outs):
         ref = eng.infer_host(x, scales)
         assert o.numpy().tobytes() == ref.tobytes()
+
+
+def test_engine_pool_matches_single_engine(eng):
+    from smap_b200.engine import RECORD_BYTES, EnginePool, scale_row
+
+    pool = EnginePool(2, 0, max_batch=2, in_h=512, in_w=832)
+    pool.load_state_dict(schema.make_state_dict(0, "identity"))
+    sc = lift_numpy.default_scale(1920, 1080)
+    scales = torch.from_numpy(np.stack([scale_row(sc)] * 2)).pin_memory()
+    xs = [schema.make_input(2, 512, 832, seed=40 + i).pin_memory() for i in range(5)]
+    outs = [torch.zeros(2, RECORD_BYTES, dtype=torch.uint8).pin_memory() for _ in range(5)]
+    tickets = [pool.submit(x, scales, o) for x, o in zip(xs, outs)]
+    for t in tickets:
+        if t in pool._tickets:
+            pool.result(t)
+    for t, (x, o) in enumerate(zip(xs, outs)):
+        # bit-identical to the synchronous call on the handle that served the ticket (tile shapes are autotuned per
+        # handle, so two handles may differ in the last bit of the backbone tensors) ...
+        ref = pool.engines[t % 2].infer_host(x, scales)
+        assert o.numpy().tobytes() == ref.tobytes()
+        # ... and equivalent to any other handle
+        other = eng.infer_host(x, scales)
+        assert np.array_equal(ref["count"], other["count"])
+    pool.close()
