@@ -105,3 +105,22 @@ def test_engine_pool_matches_single_engine(eng):
         other = eng.infer_host(x, scales)
         assert np.array_equal(ref["count"], other["count"])
     pool.close()
+
+
+def test_forward_is_bit_stable_under_concurrent_gpu_load(eng):
+    """Regression: the epilogue ring of conv_tc_kernel is refilled by TMA (async proxy) after generic-proxy reads; without
+    a proxy fence before the release, a refill overtook in-flight reads when another stream kept HBM busy and single
+    16-byte units of a residual row came back from the NEXT chunk.  A forward must not depend on what else runs."""
+    x = schema.make_input(2, 512, 832, seed=50).cuda()
+    ref = [t.clone() for t in eng.forward(x)]
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    big = torch.randn(64 * 1024 * 1024, device="cuda")
+    for rnd in range(12):
+        with torch.cuda.stream(side):
+            for _ in range(20):
+                big * 1.0001 + 1.0
+        out = eng.forward(x)
+        torch.cuda.synchronize()
+        for a, b in zip(out, ref):
+            assert torch.equal(a, b), "round %d: forward changed under concurrent load" % rnd
