@@ -112,6 +112,37 @@ int smapb_submit_host(smapb_handle* h, int slot, const float* imgs_nchw_host, co
                       smapb_record* records_host);
 int smapb_wait(smapb_handle* h, int slot);
 
+/* ---- RefineNet post-processing (optional; the reference enables it with `-rp`, exps/stage3_root2/test.sh) ------- */
+/* Replaces: refine_model.load_state_dict(torch.load(path)) (exps/stage3_root2/test.py:213-214) for model/refinenet.py:
+ * keys "block.layer{1..4}.0.{weight,bias}" (Linear), "block.layer{1..4}.1.{weight,bias,running_mean,running_var}"
+ * (BatchNorm1d), "block.layer5.{weight,bias}"; num_batches_tracked is accepted and ignored. */
+int smapb_refine_load_weight(smapb_handle* h, const char* key, const float* host, const int64_t* shape, int ndim);
+/* BN folding (eval mode, eps 1e-5) + transposition; must follow the last smapb_refine_load_weight. */
+int smapb_refine_finalize(smapb_handle* h);
+/* Replaces: refine_model(inp) (model/refinenet.py:19-26, eval): in fp32 [n,75] -> out fp32 [n,45], device pointers. */
+int smapb_refine_mlp(smapb_handle* h, const float* in_dev, int n, float* out_dev, void* stream);
+/* Replaces: lift_and_refine_3d_pose (exps/stage3_root2/test_util.py:102-131) for a batch of images, device-resident:
+ * pred2d fp32 [B,127,15,4], pred3d fp64 [B,127,15,4], counts int32 [B] (the outputs of smapb_lift3d) ->
+ * refined fp64 [B,127,15,4] = (X,Y,Z,score), rows >= counts[b] untouched.  refined may alias pred3d. */
+int smapb_refine3d(smapb_handle* h, const float* pred2d_dev, const double* pred3d_dev, const int* counts_dev, int B,
+                   int root_idx, double* refined_dev, void* stream);
+/* enable != 0: smapb_infer_device / _host / smapb_submit_host run the refinement after the lift and store the refined
+ * poses in smapb_record.pred3d, as generate_3d_point_pairs saves new_pred_bodys_3d (exps/stage3_root2/test.py:136-145). */
+int smapb_set_refine(smapb_handle* h, int enable);
+
+/* ---- result serialisation (host only, no GPU work) ------------------------------------------------------- */
+/* Replaces: result = {'model_pattern': cfg.DATASET.NAME, '3d_pairs': []} ... save_result(...) per image ...
+ * json.dump(result, f) (exps/stage3_root2/test.py:32-34,145,147-152; exps/stage3_root2/test_util.py:146-158) for the
+ * run_inference mode (no ground truth).  The file is byte-identical to what Python's json.dump writes for the same
+ * numbers (float repr, ", " / ": " separators, ensure_ascii escaping, key order of save_result). */
+typedef struct smapb_json_writer smapb_json_writer;
+int smapb_json_open(smapb_json_writer** out, const char* path, const char* model_pattern);
+/* Appends one entry per record with count > 0 (images without persons are skipped, test.py:130-131).
+ * records_host: smapb_record[B] in host memory; image_paths: B UTF-8 strings. */
+int smapb_json_append(smapb_json_writer* w, const smapb_record* records_host, int B, const char* const* image_paths);
+/* Writes the closing brackets, closes the file and frees the writer. */
+int smapb_json_close(smapb_json_writer* w);
+
 /* ---- introspection ----------------------------------------------------------------------------- */
 /* number of kernels launched by this handle since creation */
 int64_t smapb_launch_count(const smapb_handle* h);

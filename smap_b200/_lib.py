@@ -14,6 +14,8 @@ EXPORTS = [
     "smapb_finalize_weights", "smapb_backbone_forward", "smapb_merge_scale", "smapb_assoc_extract",
     "smapb_assoc_connect", "smapb_lift3d", "smapb_infer_device", "smapb_infer_host", "smapb_launch_count",
     "smapb_plan_info", "smapb_conv_test", "smapb_profile_begin", "smapb_profile_end", "smapb_submit_host", "smapb_wait",
+    "smapb_refine_load_weight", "smapb_refine_finalize", "smapb_refine_mlp", "smapb_refine3d", "smapb_set_refine",
+    "smapb_json_open", "smapb_json_append", "smapb_json_close",
 ]
 
 _lib = None
@@ -60,6 +62,14 @@ def load():
     lib.smapb_plan_info.argtypes = [vp, i32, c.POINTER(i32), c.POINTER(c.c_double)]
     lib.smapb_conv_test.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp,
                                     c.POINTER(c.c_float), vp]
+    lib.smapb_refine_load_weight.argtypes = [vp, c.c_char_p, vp, c.POINTER(i64), i32]
+    lib.smapb_refine_finalize.argtypes = [vp]
+    lib.smapb_refine_mlp.argtypes = [vp, vp, i32, vp, vp]
+    lib.smapb_refine3d.argtypes = [vp, vp, vp, vp, i32, i32, vp, vp]
+    lib.smapb_set_refine.argtypes = [vp, i32]
+    lib.smapb_json_open.argtypes = [c.POINTER(vp), c.c_char_p, c.c_char_p]
+    lib.smapb_json_append.argtypes = [vp, vp, i32, c.POINTER(c.c_char_p)]
+    lib.smapb_json_close.argtypes = [vp]
     for name in EXPORTS:
         fn = getattr(lib, name)
         if fn.restype is c.c_int and name not in ("smapb_version",):

@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libsmap_b200.so")
-SOURCES = ["engine.cu", "assoc.cu", "elementwise.cu"]
+SOURCES = ["engine.cu", "assoc.cu", "elementwise.cu", "refine.cu", "json_out.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
 
@@ -22,7 +22,7 @@ def build(force=False, verbose=False):
     objs = []
     for s in SOURCES:
         src = os.path.join(CSRC, s)
-        obj = os.path.join(LIBDIR, s.replace(".cu", ".o"))
+        obj = os.path.join(LIBDIR, os.path.splitext(s)[0] + ".o")
         objs.append(obj)
         if force or not os.path.exists(obj) or any(_newer(d, obj) for d in deps):
             cmd = ["nvcc"] + NVCC_FLAGS + ["-c", src, "-o", obj]

@@ -16,6 +16,7 @@
 #include "assoc.h"
 #include "conv_tc.cuh"
 #include "elementwise.h"
+#include "refine.h"
 
 using namespace smapb;
 
@@ -167,6 +168,11 @@ struct smapb_handle {
         cudaGraphExec_t exec;
     };
     std::vector<GraphEntry> graphs;  // whole-path CUDA graphs keyed by (B, flip, input pointers)
+    // RefineNet (optional post-processing step)
+    std::map<std::string, std::vector<float>> refine_raw;
+    float* refine_buf = nullptr;  // folded, transposed weights + biases of the five layers
+    RefineWeights refine_w{};
+    bool refine_ready = false, refine_on = false;
     std::map<std::pair<int, int>, int> eager_runs;  // (B, flip) -> number of eager executions so far
     // profiling (per-op CUDA events on the launching stream)
     bool profiling = false;
@@ -1100,6 +1106,7 @@ void smapb_destroy(smapb_handle* h) {
                     h->rootd, h->scratch_detd, h->scratch_rootd, h->scales_dev, h->records_dev, h->stem_w, h->stem_b};
     for (void* p : ptrs)
         if (p) cudaFree(p);
+    if (h->refine_buf) cudaFree(h->refine_buf);
     delete h;
 }
 
@@ -1360,6 +1367,102 @@ int smapb_lift3d(smapb_handle* h, const float* bodies, const int* counts, const 
     return 0;
 }
 
+// ---- RefineNet ---------------------------------------------------------------------------------
+int smapb_refine_load_weight(smapb_handle* h, const char* key, const float* host, const int64_t* shape, int ndim) {
+    if (!h || !key || !host) return -1;
+    const std::string k(key);
+    if (k.size() > 19 && k.compare(k.size() - 19, 19, "num_batches_tracked") == 0) return 0;
+    size_t n = 1;
+    for (int i = 0; i < ndim; i++) n *= (size_t)shape[i];
+    h->refine_raw[k].assign(host, host + n);
+    h->refine_ready = false;
+    return 0;
+}
+
+int smapb_refine_finalize(smapb_handle* h) {
+    if (!h) return -1;
+    cudaSetDevice(h->device);
+    static const int dims[RF_LAYERS + 1] = {75, 160, 256, 256, 128, 45};
+    size_t total = 0;
+    for (int l = 0; l < RF_LAYERS; l++) total += (size_t)dims[l] * dims[l + 1] + dims[l + 1];
+    std::vector<float> buf(total);
+    size_t off = 0, w_off[RF_LAYERS], b_off[RF_LAYERS];
+    for (int l = 0; l < RF_LAYERS; l++) {
+        const int K = dims[l], N = dims[l + 1];
+        const bool has_bn = l < RF_LAYERS - 1;
+        const std::string lp = "block.layer" + std::to_string(l + 1) + (has_bn ? ".0." : ".");
+        const std::string bp = "block.layer" + std::to_string(l + 1) + ".1.";
+        auto get = [&](const std::string& key, size_t n, const std::vector<float>** out) -> int {
+            auto it = h->refine_raw.find(key);
+            if (it == h->refine_raw.end()) return fail(h, -3, "smapb_refine_finalize: missing key " + key);
+            if (it->second.size() != n) return fail(h, -3, "smapb_refine_finalize: wrong size for " + key);
+            *out = &it->second;
+            return 0;
+        };
+        const std::vector<float>*w = nullptr, *b = nullptr, *g = nullptr, *be = nullptr, *mu = nullptr, *var = nullptr;
+        int rc = get(lp + "weight", (size_t)K * N, &w);
+        if (!rc) rc = get(lp + "bias", N, &b);
+        if (!rc && has_bn) rc = get(bp + "weight", N, &g);
+        if (!rc && has_bn) rc = get(bp + "bias", N, &be);
+        if (!rc && has_bn) rc = get(bp + "running_mean", N, &mu);
+        if (!rc && has_bn) rc = get(bp + "running_var", N, &var);
+        if (rc) return rc;
+        w_off[l] = off;
+        b_off[l] = off + (size_t)K * N;
+        for (int n = 0; n < N; n++) {
+            // BatchNorm1d(eval), eps 1e-5 (model/refinenet.py:9): y = (Wx + b - mu) * g / sqrt(var + eps) + beta
+            const double sc = has_bn ? (double)(*g)[n] / sqrt((double)(*var)[n] + 1e-5) : 1.0;
+            for (int k = 0; k < K; k++) buf[w_off[l] + (size_t)k * N + n] = (float)((double)(*w)[(size_t)n * K + k] * sc);
+            buf[b_off[l] + n] = has_bn ? (float)(((double)(*b)[n] - (double)(*mu)[n]) * sc + (double)(*be)[n]) : (*b)[n];
+        }
+        off += (size_t)K * N + N;
+    }
+    if (!h->refine_buf) CK(cudaMalloc((void**)&h->refine_buf, total * sizeof(float)));
+    CK(cudaMemcpy(h->refine_buf, buf.data(), total * sizeof(float), cudaMemcpyHostToDevice));
+    for (int l = 0; l < RF_LAYERS; l++) {
+        h->refine_w.w[l] = h->refine_buf + w_off[l];
+        h->refine_w.b[l] = h->refine_buf + b_off[l];
+    }
+    h->refine_ready = true;
+    return 0;
+}
+
+int smapb_set_refine(smapb_handle* h, int enable) {
+    if (!h) return -1;
+    if (enable && !h->refine_ready) return fail(h, -2, "smapb_set_refine: RefineNet weights not finalized");
+    if ((enable != 0) != h->refine_on) {  // captured graphs contain (or lack) the refine launch
+        cudaSetDevice(h->device);
+        cudaDeviceSynchronize();
+        for (auto& g : h->graphs) cudaGraphExecDestroy(g.exec);
+        h->graphs.clear();
+    }
+    h->refine_on = enable != 0;
+    return 0;
+}
+
+int smapb_refine_mlp(smapb_handle* h, const float* in_dev, int n, float* out_dev, void* stream) {
+    if (!h) return -1;
+    if (!h->refine_ready) return fail(h, -2, "smapb_refine_mlp: RefineNet weights not finalized");
+    if (n < 0) return fail(h, -1, "smapb_refine_mlp: n < 0");
+    cudaSetDevice(h->device);
+    CK(launch_refine_mlp(h->refine_w, in_dev, n, out_dev, (cudaStream_t)stream));
+    if (n) h->launches++;
+    return 0;
+}
+
+int smapb_refine3d(smapb_handle* h, const float* pred2d, const double* pred3d, const int* counts, int B, int root_idx,
+                   double* refined, void* stream) {
+    if (!h) return -1;
+    if (!h->refine_ready) return fail(h, -2, "smapb_refine3d: RefineNet weights not finalized");
+    if (B < 1) return fail(h, -1, "B < 1");
+    if (root_idx < 0 || root_idx >= NJ) return fail(h, -1, "root_idx outside [0, 15)");
+    cudaSetDevice(h->device);
+    CK(launch_refine_records(h->refine_w, pred2d, pred3d, counts, B, root_idx, (long long)MAXP * NJ * 4, (long long)MAXP * NJ * 4,
+                             1, refined, (long long)MAXP * NJ * 4, (cudaStream_t)stream));
+    h->launches++;
+    return 0;
+}
+
 // flip along W of an NCHW fp32 batch (torch.flip(imgs, [-1]), exps/stage3_root2/test.py:56)
 __global__ void flip_w_kernel(const float* __restrict__ in, float* __restrict__ out, long long rows, int W) {
     const long long total = rows * W;
@@ -1430,6 +1533,14 @@ static int infer_body(smapb_handle* h, Plan* plan, const float* imgs, const doub
                    sizeof(smapb_record) / 8, sizeof(smapb_record) / 8, sizeof(smapb_record) / 4, st));
     prof_mark(h, PK_LIFT, st, "lift");
     h->launches += 5;
+    if (h->refine_on) {  // refined poses replace pred3d, as save_result(pred_bodys_2d, new_pred_bodys_3d, ...) does (test.py:137-145)
+        double* p3 = reinterpret_cast<double*>(rb + offsetof(smapb_record, pred3d));
+        CK(launch_refine_records(h->refine_w, reinterpret_cast<float*>(rb + offsetof(smapb_record, pred2d)), p3,
+                                 reinterpret_cast<int*>(rb + offsetof(smapb_record, count)), B, 2, sizeof(smapb_record) / 4,
+                                 sizeof(smapb_record) / 8, sizeof(smapb_record) / 4, p3, sizeof(smapb_record) / 8, st));
+        prof_mark(h, PK_LIFT, st, "refine");
+        h->launches++;
+    }
     return 0;
 }
 
@@ -1480,7 +1591,7 @@ int smapb_infer_device(smapb_handle* h, const float* imgs, const double* scales,
         ge = &h->graphs.back();
     }
     CK(cudaGraphLaunch(ge->exec, st));
-    h->launches += (int64_t)plan->ops.size() * (do_flip ? 2 : 1) + 5 + (do_flip ? 1 : 0);
+    h->launches += (int64_t)plan->ops.size() * (do_flip ? 2 : 1) + 5 + (do_flip ? 1 : 0) + (h->refine_on ? 1 : 0);
     if (records != h->records_dev)
         CK(cudaMemcpyAsync(records, h->records_dev, (size_t)B * sizeof(smapb_record), cudaMemcpyDeviceToDevice, st));
     return 0;

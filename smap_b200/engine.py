@@ -129,6 +129,37 @@ class Engine:
                                           _ptr(rdp), _ptr(co), _stream()), "smapb_lift3d")
         return p2, p3, rdp, co
 
+    # ---- RefineNet (optional post-processing) ---------------------------------------------------
+    def load_refine_state_dict(self, sd):
+        """sd: state dict of the reference model/refinenet.py RefineNet (block.layerN...)."""
+        for k, v in sd.items():
+            if k.endswith("num_batches_tracked"):
+                continue
+            a = v.detach().cpu().float().contiguous().numpy() if torch.is_tensor(v) else np.ascontiguousarray(v, np.float32)
+            shape = (ctypes.c_int64 * max(1, a.ndim))(*a.shape)
+            self._check(self.lib.smapb_refine_load_weight(self._h, k.encode(), a.ctypes.data_as(ctypes.c_void_p), shape, a.ndim),
+                        "smapb_refine_load_weight(%s)" % k)
+        self._check(self.lib.smapb_refine_finalize(self._h), "smapb_refine_finalize")
+
+    def refine_mlp(self, inp):
+        """inp fp32 cuda [n,75] -> fp32 cuda [n,45] (refine_model(inp), model/refinenet.py:19-26)."""
+        inp = inp.contiguous()
+        out = torch.empty(inp.shape[0], 45, device=inp.device)
+        self._check(self.lib.smapb_refine_mlp(self._h, _ptr(inp), inp.shape[0], _ptr(out), _stream()), "smapb_refine_mlp")
+        return out
+
+    def refine(self, pred2d, pred3d, counts, root_idx=2):
+        """outputs of lift() -> refined fp64 cuda [B,127,15,4] (lift_and_refine_3d_pose, test_util.py:102-131); rows
+        >= counts[b] are zero."""
+        out = torch.zeros_like(pred3d)
+        self._check(self.lib.smapb_refine3d(self._h, _ptr(pred2d.contiguous()), _ptr(pred3d.contiguous()), _ptr(counts),
+                                            pred3d.shape[0], root_idx, _ptr(out), _stream()), "smapb_refine3d")
+        return out
+
+    def set_refine(self, enable=True):
+        """infer_device / infer_host / submit_host store the refined poses in the records' pred3d field."""
+        self._check(self.lib.smapb_set_refine(self._h, int(bool(enable))), "smapb_set_refine")
+
     # ---- whole path ---------------------------------------------------------------------------
     def infer_device(self, imgs, scales, do_flip=False):
         """imgs cuda fp32 [B,3,H,W], scales cuda f64 [B,9] -> records uint8 cuda [B, RECORD_BYTES]."""

@@ -21,3 +21,23 @@ def lift_case_inputs(ci):
     det_d = rng.normal(0, 20, (14, 128, 208)).astype(np.float32)
     root_d = rng.uniform(1, 9, (128, 208)).astype(np.float32)
     return b, det_d, root_d, GEOMS[ci % 4]
+
+
+def refine_state_dict(seed=7):
+    """Seeded RefineNet weights with non-trivial BatchNorm statistics (pure generator: keys/shapes follow
+    model/refinenet.py:8-17).  -> {key: float32 ndarray}"""
+    rng = np.random.default_rng(seed)
+    layers = [(75, 160), (160, 256), (256, 256), (256, 128)]
+    sd = {}
+    for i, (k, n) in enumerate(layers, start=1):
+        p = "block.layer%d." % i
+        sd[p + "0.weight"] = (rng.uniform(-1, 1, (n, k)) / np.sqrt(k)).astype(np.float32)
+        sd[p + "0.bias"] = rng.uniform(-0.1, 0.1, n).astype(np.float32)
+        sd[p + "1.weight"] = rng.uniform(0.5, 1.5, n).astype(np.float32)
+        sd[p + "1.bias"] = rng.normal(0, 0.2, n).astype(np.float32)
+        sd[p + "1.running_mean"] = rng.normal(0, 0.3, n).astype(np.float32)
+        sd[p + "1.running_var"] = rng.uniform(0.5, 2.0, n).astype(np.float32)
+        sd[p + "1.num_batches_tracked"] = np.asarray(100, np.int64)
+    sd["block.layer5.weight"] = (rng.uniform(-1, 1, (45, 128)) / np.sqrt(128)).astype(np.float32)
+    sd["block.layer5.bias"] = rng.uniform(-0.1, 0.1, 45).astype(np.float32)
+    return sd

@@ -69,7 +69,8 @@ def golden_backbone():
     print("backbone golden:", {k: v.shape for k, v in out.items()})
 
 
-def golden_lift():
+def _reference_env():
+    """numpy aliases, PROJECT_HOME and an easydict stub so that exps/stage3_root2/test_util.py imports here."""
     np.int = int
     np.float = float
     os.environ.setdefault("PROJECT_HOME", "/tmp/smap_project_home")
@@ -84,6 +85,10 @@ def golden_lift():
 
     ed.EasyDict = EasyDict
     sys.modules["easydict"] = ed
+
+
+def golden_lift():
+    _reference_env()
     import cv2
     import test_util as T
 
@@ -122,6 +127,61 @@ def golden_lift():
     print("lift golden:", N_LIFT_CASES, "cases")
 
 
+def golden_refine():
+    """refine_cases.npz: outputs of the unmodified model/refinenet.py + test_util.lift_and_refine_3d_pose on the lift
+    goldens (the 2D/3D poses the reference lift produced), with seeded weights."""
+    _reference_env()
+    import test_util as T
+    from model.refinenet import RefineNet
+
+    from cases import N_LIFT_CASES, refine_state_dict
+
+    lift = np.load(os.path.join(HERE, "lift_cases.npz"))
+    net = RefineNet().eval()
+    net.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in refine_state_dict().items()})
+    out = {}
+    with torch.no_grad():
+        for ci in range(N_LIFT_CASES):
+            p2, p3 = lift["c%d_pred2d" % ci], lift["c%d_pred3d" % ci]
+            if len(p3) == 0:
+                out["c%d_refined" % ci] = np.zeros((0, 15, 4), np.float64)
+                continue
+            out["c%d_refined" % ci] = np.asarray(T.lift_and_refine_3d_pose(p2.copy(), p3.copy(), net, torch.device("cpu"), root_n=2),
+                                                 np.float64)
+    np.savez_compressed(os.path.join(HERE, "refine_cases.npz"), **out)
+    print("refine golden:", {k: v.shape for k, v in list(out.items())[:4]})
+
+
+def golden_results_json():
+    """results_json.txt: json.dump of the dict the unmodified save_result builds (test_util.py:146-158) from the seeded
+    records of tests/test_results_json.py::make_records(1, 7)."""
+    _reference_env()
+    import json
+
+    import test_util as T
+
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_results_json import make_records
+
+    rec = make_records(1, 7)
+    result = {"model_pattern": "CMU", "3d_pairs": []}
+    for b in range(len(rec)):
+        n = int(rec["count"][b])
+        if n == 0:
+            continue  # test.py:130-131
+        T.save_result(rec["pred2d"][b, :n], rec["pred3d"][b, :n], None, rec["root_depth"][b, :n], "img_%d.jpg" % b, result)
+    with open(os.path.join(HERE, "results_json.txt"), "w") as f:
+        json.dump(result, f)
+    print("results json golden:", len(result["3d_pairs"]), "pairs")
+
+
 if __name__ == "__main__":
-    golden_backbone()
-    golden_lift()
+    which = sys.argv[1:] or ["backbone", "lift", "refine", "json"]
+    if "json" in which:
+        golden_results_json()
+    if "backbone" in which:
+        golden_backbone()
+    if "lift" in which:
+        golden_lift()
+    if "refine" in which:
+        golden_refine()
