@@ -48,6 +48,20 @@ int smapb_load_weight(smapb_handle* h, const char* key, const float* host, const
  * execution plan.  precision: SMAPB_PREC_*.  Must be called once after all weights are loaded. */
 int smapb_finalize_weights(smapb_handle* h, int precision);
 
+/* ---- pre-processing (the step in front of the backbone) ------------------------------------------------------ */
+/* Replaces: CustomDataset.__getitem__ after cv2.imread (dataset/custom_dataset.py:27-68): scale = min(net_w/W, net_h/H),
+ * cv2.resize(img, (0,0), fx=scale, fy=scale) (8-bit INTER_LINEAR, bit-exact incl. the 1/2-scale INTER_AREA reroute),
+ * gray-128 letterbox to net_w x net_h, torchvision ToTensor + Normalize(cfg.INPUT.MEANS, cfg.INPUT.STDS).
+ * bgr_dev: uint8 [img_h, img_w, 3] (BGR, as cv2.imread returns); out_nchw_dev: fp32 [3, in_h, in_w] - one image slot of the
+ * batch handed to smapb_backbone_forward / smapb_infer_device.  scale_row_host (may be NULL): the image's 9 scale values
+ * in SMAPB_SCALE_LEN order, including the default intrinsics of exps/stage3_root2/test.py:99-103. */
+int smapb_preprocess(smapb_handle* h, const uint8_t* bgr_dev, int img_h, int img_w, float* out_nchw_dev, double* scale_row_host,
+                     void* stream);
+/* Same with the image in host memory (pinned for an asynchronous copy): uploads the uint8 pixels - 4x fewer bytes than
+ * the fp32 tensor the reference's loader ships - into the handle's staging buffer first. */
+int smapb_preprocess_host(smapb_handle* h, const uint8_t* bgr_host, int img_h, int img_w, float* out_nchw_dev,
+                          double* scale_row_host, void* stream);
+
 /* ---- backbone -------------------------------------------------------------------------------- */
 /* Replaces: SMAP.forward inference branch (model/smap.py:403-419).
  * imgs_nchw_dev: fp32 [B,3,in_h,in_w] (normalised BGR).  Outputs fp32 NCHW:

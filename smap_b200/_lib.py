@@ -15,7 +15,7 @@ EXPORTS = [
     "smapb_assoc_connect", "smapb_lift3d", "smapb_infer_device", "smapb_infer_host", "smapb_launch_count",
     "smapb_plan_info", "smapb_conv_test", "smapb_profile_begin", "smapb_profile_end", "smapb_submit_host", "smapb_wait",
     "smapb_refine_load_weight", "smapb_refine_finalize", "smapb_refine_mlp", "smapb_refine3d", "smapb_set_refine",
-    "smapb_json_open", "smapb_json_append", "smapb_json_close",
+    "smapb_json_open", "smapb_json_append", "smapb_json_close", "smapb_preprocess", "smapb_preprocess_host",
 ]
 
 _lib = None
@@ -67,6 +67,8 @@ def load():
     lib.smapb_refine_mlp.argtypes = [vp, vp, i32, vp, vp]
     lib.smapb_refine3d.argtypes = [vp, vp, vp, vp, i32, i32, vp, vp]
     lib.smapb_set_refine.argtypes = [vp, i32]
+    lib.smapb_preprocess.argtypes = [vp, vp, i32, i32, vp, c.POINTER(c.c_double), vp]
+    lib.smapb_preprocess_host.argtypes = [vp, vp, i32, i32, vp, c.POINTER(c.c_double), vp]
     lib.smapb_json_open.argtypes = [c.POINTER(vp), c.c_char_p, c.c_char_p]
     lib.smapb_json_append.argtypes = [vp, vp, i32, c.POINTER(c.c_char_p)]
     lib.smapb_json_close.argtypes = [vp]

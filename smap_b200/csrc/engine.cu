@@ -16,6 +16,7 @@
 #include "assoc.h"
 #include "conv_tc.cuh"
 #include "elementwise.h"
+#include "preprocess.h"
 #include "refine.h"
 
 using namespace smapb;
@@ -168,6 +169,15 @@ struct smapb_handle {
         cudaGraphExec_t exec;
     };
     std::vector<GraphEntry> graphs;  // whole-path CUDA graphs keyed by (B, flip, input pointers)
+    // pre-processing: resampling tables per source geometry, staging for host images
+    struct PreEntry {
+        ResizePlan plan;
+        ResizeTablesDev tab{};
+        void* buf = nullptr;
+    };
+    std::map<std::pair<int, int>, PreEntry> pre_cache;
+    uint8_t* pre_stage = nullptr;
+    size_t pre_stage_bytes = 0;
     // RefineNet (optional post-processing step)
     std::map<std::string, std::vector<float>> refine_raw;
     float* refine_buf = nullptr;  // folded, transposed weights + biases of the five layers
@@ -1107,6 +1117,8 @@ void smapb_destroy(smapb_handle* h) {
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (h->refine_buf) cudaFree(h->refine_buf);
+    if (h->pre_stage) cudaFree(h->pre_stage);
+    for (auto& e : h->pre_cache) cudaFree(e.second.buf);
     delete h;
 }
 
@@ -1365,6 +1377,82 @@ int smapb_lift3d(smapb_handle* h, const float* bodies, const int* counts, const 
                    (long long)MAXP * NJ * 4, (long long)MAXP * NJ * 4, MAXP, 1, (cudaStream_t)stream));
     h->launches++;
     return 0;
+}
+
+// ---- pre-processing ---------------------------------------------------------------------------
+static int pre_entry(smapb_handle* h, int img_h, int img_w, smapb_handle::PreEntry** out) {
+    if (img_h < 2 || img_w < 2 || img_h > 16384 || img_w > 16384) return fail(h, -1, "smapb_preprocess: image size outside [2, 16384]");
+    auto key = std::make_pair(img_w, img_h);
+    auto it = h->pre_cache.find(key);
+    if (it == h->pre_cache.end()) {
+        if (h->pre_cache.size() >= 256) {  // bound the cache: drop everything (streams are idle after the sync)
+            cudaDeviceSynchronize();
+            for (auto& e : h->pre_cache) cudaFree(e.second.buf);
+            h->pre_cache.clear();
+        }
+        smapb_handle::PreEntry E;
+        make_resize_plan(img_w, img_h, h->in_w, h->in_h, &E.plan);
+        const ResizePlan& P = E.plan;
+        const size_t nx = P.xofs.size(), ny = P.yofs.size();  // ny = 2 * dst_h
+        const size_t bytes = nx * 4 + ny * 4 + nx * 2 * 2 + ny * 2 + 64;
+        CK(cudaMalloc(&E.buf, bytes));
+        char* d = (char*)E.buf;
+        int* xo = (int*)d;
+        int* yo = xo + nx;
+        short* xc = (short*)(yo + ny);
+        short* yc = xc + 2 * nx;
+        CK(cudaMemcpy(xo, P.xofs.data(), nx * 4, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(yo, P.yofs.data(), ny * 4, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(xc, P.xcoef.data(), nx * 2 * 2, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(yc, P.ycoef.data(), ny * 2, cudaMemcpyHostToDevice));
+        E.tab = {xo, xc, yo, yc};
+        it = h->pre_cache.emplace(key, std::move(E)).first;
+    }
+    *out = &it->second;
+    return 0;
+}
+
+static void pre_scale_row(const smapb_handle* h, const ResizePlan& P, double* row) {
+    if (!row) return;
+    row[0] = P.scale;             // scale['scale']                    (dataset/custom_dataset.py:46)
+    row[1] = P.src_w;             // img_width, img_height              (:49-50)
+    row[2] = P.src_h;
+    row[3] = h->in_w;             // net_width, net_height              (:51-52)
+    row[4] = h->in_h;
+    row[5] = P.src_w;             // f_x = f_y = img_width              (exps/stage3_root2/test.py:100-101)
+    row[6] = P.src_w;
+    row[7] = P.src_w / 2.0;       // cx, cy                             (test.py:102-103)
+    row[8] = P.src_h / 2.0;
+}
+
+int smapb_preprocess(smapb_handle* h, const uint8_t* bgr_dev, int img_h, int img_w, float* out_nchw_dev, double* scale_row_host,
+                     void* stream) {
+    if (!h || !bgr_dev || !out_nchw_dev) return -1;
+    cudaSetDevice(h->device);
+    smapb_handle::PreEntry* E = nullptr;
+    int rc = pre_entry(h, img_h, img_w, &E);
+    if (rc) return rc;
+    CK(launch_preprocess(bgr_dev, E->plan, E->tab, h->in_w, h->in_h, out_nchw_dev, (cudaStream_t)stream));
+    h->launches++;
+    pre_scale_row(h, E->plan, scale_row_host);
+    return 0;
+}
+
+int smapb_preprocess_host(smapb_handle* h, const uint8_t* bgr_host, int img_h, int img_w, float* out_nchw_dev,
+                          double* scale_row_host, void* stream) {
+    if (!h || !bgr_host || !out_nchw_dev) return -1;
+    cudaSetDevice(h->device);
+    const size_t bytes = (size_t)img_h * img_w * 3;
+    if (bytes > h->pre_stage_bytes) {
+        cudaDeviceSynchronize();
+        if (h->pre_stage) cudaFree(h->pre_stage);
+        h->pre_stage = nullptr;
+        h->pre_stage_bytes = 0;
+        CK(cudaMalloc((void**)&h->pre_stage, bytes));
+        h->pre_stage_bytes = bytes;
+    }
+    CK(cudaMemcpyAsync(h->pre_stage, bgr_host, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    return smapb_preprocess(h, h->pre_stage, img_h, img_w, out_nchw_dev, scale_row_host, stream);
 }
 
 // ---- RefineNet ---------------------------------------------------------------------------------

@@ -129,6 +129,30 @@ class Engine:
                                           _ptr(rdp), _ptr(co), _stream()), "smapb_lift3d")
         return p2, p3, rdp, co
 
+    # ---- pre-processing ------------------------------------------------------------------------
+    def preprocess(self, images, out=None):
+        """images: list of uint8 BGR [H,W,3] tensors (cuda or cpu; numpy arrays are taken as host images) ->
+        (imgs fp32 cuda [B,3,in_h,in_w], scales float64 cpu [B,9]); dataset/custom_dataset.py:27-68 + test.py:99-103."""
+        B = len(images)
+        dev = self.device
+        if out is None:
+            out = torch.empty(B, 3, self.in_h, self.in_w, device=dev)
+        scales = np.zeros((B, 9), np.float64)
+        keep = []
+        for b, im in enumerate(images):
+            if not torch.is_tensor(im):
+                im = torch.from_numpy(np.ascontiguousarray(im))
+            assert im.dtype == torch.uint8 and im.dim() == 3 and im.shape[2] == 3, "uint8 BGR [H,W,3] expected"
+            im = im.contiguous()
+            keep.append(im)
+            row = scales[b].ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+            fn = self.lib.smapb_preprocess if im.is_cuda else self.lib.smapb_preprocess_host
+            self._check(fn(self._h, _ptr(im), im.shape[0], im.shape[1], ctypes.c_void_p(out[b].data_ptr()), row, _stream()),
+                        "smapb_preprocess")
+        if any(not im.is_cuda for im in keep):
+            torch.cuda.current_stream().synchronize()  # host images must outlive their asynchronous upload
+        return out, torch.from_numpy(scales)
+
     # ---- RefineNet (optional post-processing) ---------------------------------------------------
     def load_refine_state_dict(self, sd):
         """sd: state dict of the reference model/refinenet.py RefineNet (block.layerN...)."""

@@ -41,3 +41,18 @@ def refine_state_dict(seed=7):
     sd["block.layer5.weight"] = (rng.uniform(-1, 1, (45, 128)) / np.sqrt(128)).astype(np.float32)
     sd["block.layer5.bias"] = rng.uniform(-0.1, 0.1, 45).astype(np.float32)
     return sd
+
+
+PRE_GEOMS = [(1920, 1080), (640, 480), (1000, 1500), (832, 512), (1664, 1024), (1280, 720), (333, 517), (2592, 1944),
+             (500, 300), (831, 511), (1665, 1025), (100, 60), (2048, 1024), (416, 256), (3840, 2160), (517, 333)]
+
+
+def preprocess_case_image(ci):
+    """Seeded uint8 BGR test image [H,W,3] for geometry PRE_GEOMS[ci]: smooth low-frequency structure (so that the
+    bilinear weights matter) plus full-range noise (so that every rounding case occurs)."""
+    W, H = PRE_GEOMS[ci]
+    rng = np.random.default_rng(500 + ci)
+    yy, xx = np.mgrid[0:H, 0:W].astype(np.float32)
+    base = 127 + 90 * np.sin(xx / (7 + ci))[:, :, None] * np.cos(yy / (11 + ci))[:, :, None] * np.array([1, 0.7, -0.8], np.float32)
+    img = base + rng.normal(0, 40, (H, W, 3))
+    return np.clip(np.rint(img), 0, 255).astype(np.uint8)

@@ -175,8 +175,41 @@ def golden_results_json():
     print("results json golden:", len(result["3d_pairs"]), "pairs")
 
 
+def golden_preprocess():
+    """preprocess_digests.json: SHA-256 of the float32 [3,512,832] tensors (and the scale dicts) the unmodified
+    dataset/custom_dataset.py CustomDataset.aug_croppad + its torchvision transform produce for the seeded images of
+    cases.preprocess_case_image; preprocess_small.npz: one full output (416x256 source) for a value-level comparison."""
+    _reference_env()
+    import hashlib
+    import json
+
+    from dataset.custom_dataset import CustomDataset
+
+    from cases import PRE_GEOMS, preprocess_case_image
+
+    cfg = NS(INPUT=NS(MEANS=[0.406, 0.456, 0.485], STDS=[0.225, 0.224, 0.229]))
+    ds = CustomDataset(cfg, "/nonexistent_dataset_dir")
+    out = {}
+    for ci, (W, H) in enumerate(PRE_GEOMS):
+        img = preprocess_case_image(ci)
+        ds.image_shape = (img.shape[1], img.shape[0])     # custom_dataset.py:31
+        net_img, scale = ds.aug_croppad(img)              # custom_dataset.py:33
+        t = ds.transform(net_img).numpy()                 # custom_dataset.py:34
+        assert t.shape == (3, 512, 832) and t.dtype == np.float32
+        out["c%d" % ci] = {"geom": [W, H], "sha256": hashlib.sha256(np.ascontiguousarray(t).tobytes()).hexdigest(),
+                           "u8_sha256": hashlib.sha256(np.ascontiguousarray(net_img).tobytes()).hexdigest(),
+                           "scale": {k: float(v) for k, v in scale.items()}}
+        if (W, H) == (416, 256):
+            np.savez_compressed(os.path.join(HERE, "preprocess_small.npz"), tensor=t[:, ::4, ::4].copy(), ci=ci)
+    with open(os.path.join(HERE, "preprocess_digests.json"), "w") as f:
+        json.dump(out, f, indent=1)
+    print("preprocess golden:", len(out), "cases")
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["backbone", "lift", "refine", "json"]
+    which = sys.argv[1:] or ["backbone", "lift", "refine", "json", "preprocess"]
+    if "preprocess" in which:
+        golden_preprocess()
     if "json" in which:
         golden_results_json()
     if "backbone" in which:
