@@ -323,8 +323,9 @@ cudaError_t launch_conv(const ConvParams& cp, int block_n, int nterms, int sm_co
         return nterms == 3 ? launch_conv_inst<BN, 3, 1>(cp, sm_count, st, pdl)          \
                            : launch_conv_inst<BN, 1, 1>(cp, sm_count, st, pdl);
     switch (block_n) {
-        case 256:  // only the single-term mode has room for 256-wide operand stages next to the epilogue staging
-            return nterms == 1 ? launch_conv_inst<256, 1, 1>(cp, sm_count, st, pdl) : cudaErrorInvalidValue;
+        case 256:  // bf16x3: 2 x 96 KB operand stages + output staging fill the smem, no room for an epilogue-input ring
+            if (nterms == 1) return launch_conv_inst<256, 1, 1>(cp, sm_count, st, pdl);
+            return (cp.has_res + cp.n_post) ? cudaErrorInvalidValue : launch_conv_inst2<256, 3, false, 1>(cp, sm_count, st, pdl);
         SMAPB_CASE(128)
         SMAPB_CASE(64)
         SMAPB_CASE(32)
@@ -439,7 +440,10 @@ int setup_conv(smapb_handle* h, const ConvLayer& L, const Act& in, const Act* re
     if (force_bn) {  // autotuner override
         bn = force_bn;
         cg = force_cg ? force_cg : 1;
-        if (L.Cout_pad % bn || (cg == 2 && (bn != 256 || h->nterms != 3 || outf || !cg_out)) || (cg == 1 && bn == 256 && h->nterms == 3))
+        // one-CTA 128 x 256 tiles in bf16x3 have room for two 96 KB operand stages only without an epilogue-input ring
+        const bool needs_ring = res || post1 || up;
+        if (L.Cout_pad % bn || (cg == 2 && (bn != 256 || h->nterms != 3 || outf || !cg_out)) ||
+            (cg == 1 && bn == 256 && h->nterms == 3 && needs_ring))
             return fail(h, -31, "invalid forced tile");
     }
     if (cg_out) *cg_out = cg;
@@ -690,11 +694,12 @@ struct PlanBuilder {
             cudaEventCreate(&e0);
             cudaEventCreate(&e1);
             float best_ms = 1e30f;
-            const int cand[4][2] = {{128, 1}, {64, 1}, {256, 2}, {32, 1}};
+            const int cand[5][2] = {{128, 1}, {64, 1}, {256, 2}, {256, 1}, {32, 1}};
             for (auto& c : cand) {
                 if (L.Cout_pad % c[0]) continue;
                 if (c[1] == 2 && h->nterms != 3) continue;
                 if (c[0] == 32 && L.Cout_pad > 64) continue;
+                if (c[0] == 256 && c[1] == 1 && getenv("SMAPB_NO_BN256")) continue;  // A/B switch for the 128 x 256 one-CTA tiles
                 Op trial;
                 int rc2 = setup_conv(h, L, in, res, p1, p2, out, nullptr, relu, &trial.cp, &trial.block_n, &trial.flops, in2,
                                      up, &trial.cg, c[0], c[1]);

@@ -87,3 +87,23 @@ def test_conv_residual_and_post_adds_deterministic(eng, B, H, W, Cin, Cout):
     for y in ys:
         assert torch.equal(y, ys[0]), "non-deterministic output"
         assert (y - ref).abs().max().item() / ref.abs().max().item() < 2e-5
+
+
+_TILE_CASES = [(8, 32, 52, 256, 256, 3, 1), (8, 32, 52, 1024, 256, 1, 1), (2, 16, 26, 512, 512, 3, 2)]
+
+
+@pytest.mark.parametrize("tile,case", [(t, c) for t in ("128,1", "64,1", "256,1") for c in _TILE_CASES] +
+                         [("256,2", c) for c in _TILE_CASES[:2]])
+def test_every_tile_shape_gives_the_same_conv(eng, monkeypatch, tile, case):
+    """The autotuner may pick any of these (BLOCK_N, CTA-group) shapes for a ring-free layer: each must be correct."""
+    B, H, W, Cin, Cout, k, stride = case
+    g = torch.Generator(device="cpu").manual_seed(11)
+    x = torch.randn(B, H, W, Cin, generator=g).cuda()
+    w = (torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5).cuda()
+    b = torch.randn(Cout, generator=g).cuda()
+    ref = F.relu(F.conv2d(x.permute(0, 3, 1, 2), w, b, stride=stride, padding=k // 2)).permute(0, 2, 3, 1)
+    monkeypatch.setenv("SMAPB_FORCE_TILE", tile)
+    y = eng.conv_test(x, w, b, stride=stride, relu=True)
+    torch.cuda.synchronize()
+    err = (y - ref).abs().max().item() / ref.abs().max().item()
+    assert err < 2e-5, "tile %s: relative error %g" % (tile, err)
