@@ -274,6 +274,12 @@ class EnginePool:
         for e in self.engines:
             e.load_state_dict(sd, precision)
 
+    def load_refine_state_dict(self, sd, enable=True):
+        """RefineNet weights for every handle; enable=True makes the records carry the refined poses."""
+        for e in self.engines:
+            e.load_refine_state_dict(sd)
+            e.set_refine(enable)
+
     def submit(self, imgs, scales, out, do_flip=False):
         """Enqueue one host batch (pinned tensors, see Engine.submit_host); returns a ticket for result()."""
         t = self._next
