@@ -158,9 +158,7 @@ struct smapb_handle {
     std::map<std::string, std::pair<int, int>> tune_cache;  // layer geometry -> measured best (BLOCK_N, CG)
     bool autotune = getenv("SMAPB_NO_AUTOTUNE") == nullptr;
     bool two_streams = getenv("SMAPB_ONE_STREAM") == nullptr;  // side branches (heads, skip convs) on a second stream
-    cudaStream_t aux_stream = nullptr;  // second branch of the dual-stream forward
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-    bool dual = getenv("SMAPB_DUAL") != nullptr;
+    cudaStream_t aux_stream = nullptr;  // side branches of the decoder (skip convs, heads) run here
     cudaStream_t own_stream = nullptr;  // blocking stream used when the caller passes the legacy default stream
     struct GraphEntry {
         int B, flip;
@@ -966,7 +964,7 @@ int run_plan(smapb_handle* h, Plan* plan, const float* imgs, float* hm2d, float*
     prof_mark(h, PK_START, st);
     // profiling serialises everything on one stream (per-op event deltas); otherwise side-branch ops run on the
     // handle's second stream, ordered against the main chain by events on exactly the tensors they exchange
-    const bool multi = !h->profiling && !h->dual && h->aux_stream != nullptr;
+    const bool multi = !h->profiling && h->aux_stream != nullptr;
     cudaStream_t const main_st = st;
     const int stop_after = getenv("SMAPB_DEBUG_STOP") ? atoi(getenv("SMAPB_DEBUG_STOP")) : 1 << 30;
     int op_idx = 0;
@@ -1083,8 +1081,6 @@ int smapb_create(smapb_handle** out, int device, int max_batch, int in_h, int in
     }
     if (cudaStreamCreate(&h->own_stream) != cudaSuccess) h->own_stream = nullptr;
     cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking);
-    cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
     const char* aerr = nullptr;
     // association kernels stage whole planes in shared memory; larger maps are rejected at call time
     if (assoc_configure(h->h, h->w, &aerr) != 0) h->err = aerr ? aerr : "assoc_configure failed";
@@ -1566,32 +1562,9 @@ __global__ void flip_w_kernel(const float* __restrict__ in, float* __restrict__ 
     }
 }
 
-// backbone forward of B frames; in dual mode as two half-batches on two streams (fork/join), so that the tail of
-// one half's kernel (partial last wave) overlaps the head of the other half's next kernel
-static int forward_maybe_dual(smapb_handle* h, Plan* plan, const float* imgs, int B, float* hm, float* detd, float* rootd,
-                              cudaStream_t st) {
-    if (!(h->dual && B >= 2 && B % 2 == 0 && !h->profiling)) return run_plan(h, plan, imgs, hm, detd, rootd, st);
-    const int Bh = B / 2;
-    Plan *pa = nullptr, *pb = nullptr;
-    int rc = build_plan(h, Bh, &pa, 1);
-    if (!rc) rc = build_plan(h, Bh, &pb, 2);
-    if (rc) return rc;
-    const size_t hw = (size_t)h->h * h->w;
-    CK(cudaEventRecord(h->ev_fork, st));
-    CK(cudaStreamWaitEvent(h->aux_stream, h->ev_fork, 0));
-    rc = run_plan(h, pa, imgs, hm, detd, rootd, st);
-    if (rc) return rc;
-    rc = run_plan(h, pb, imgs + (size_t)Bh * 3 * h->in_h * h->in_w, hm + (size_t)Bh * NC2D * hw, detd + (size_t)Bh * NL * hw,
-                  rootd + (size_t)Bh * hw, h->aux_stream);
-    if (rc) return rc;
-    CK(cudaEventRecord(h->ev_join, h->aux_stream));
-    CK(cudaStreamWaitEvent(st, h->ev_join, 0));
-    return 0;
-}
-
 static int infer_body(smapb_handle* h, Plan* plan, const float* imgs, const double* scales, int B, int do_flip,
                       smapb_record* records, cudaStream_t st) {
-    int rc = forward_maybe_dual(h, plan, imgs, B, h->hm, h->detd, h->rootd, st);
+    int rc = run_plan(h, plan, imgs, h->hm, h->detd, h->rootd, st);
     if (rc) return rc;
     const size_t hw = (size_t)h->h * h->w;
     if (do_flip) {
@@ -1606,7 +1579,7 @@ static int infer_body(smapb_handle* h, Plan* plan, const float* imgs, const doub
         CK(cudaGetLastError());
         prof_mark(h, PK_ELEM, st, "flip_w");
         h->launches++;
-        rc = forward_maybe_dual(h, plan, h->imgs_flip, B, h->hm_flip, h->scratch_detd, h->scratch_rootd, st);
+        rc = run_plan(h, plan, h->imgs_flip, h->hm_flip, h->scratch_detd, h->scratch_rootd, st);
         if (rc) return rc;
     }
     CK(launch_merge_scale(h->hm, do_flip ? h->hm_flip : nullptr, B, h->h, h->w, 1, st));
