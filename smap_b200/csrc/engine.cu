@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "../../include/smap_b200.h"
+#include "../../include/smap_b200_debug.h"
 #include "assoc.h"
 #include "conv_tc.cuh"
 #include "elementwise.h"
@@ -966,7 +967,7 @@ int run_plan(smapb_handle* h, Plan* plan, const float* imgs, float* hm2d, float*
     // handle's second stream, ordered against the main chain by events on exactly the tensors they exchange
     const bool multi = !h->profiling && h->aux_stream != nullptr;
     cudaStream_t const main_st = st;
-    const int stop_after = getenv("SMAPB_DEBUG_STOP") ? atoi(getenv("SMAPB_DEBUG_STOP")) : 1 << 30;
+    static const int stop_after = getenv("SMAPB_DEBUG_STOP") ? atoi(getenv("SMAPB_DEBUG_STOP")) : 1 << 30;
     int op_idx = 0;
     for (const Op& op : plan->ops) {
         if (op_idx++ >= stop_after) break;
@@ -1017,7 +1018,8 @@ int run_plan(smapb_handle* h, Plan* plan, const float* imgs, float* hm2d, float*
         }
         h->launches++;
         if (multi && op.record) CK(cudaEventRecord(op.ev, st));
-        if (getenv("SMAPB_DEBUG_SYNC")) CK(cudaStreamSynchronize(st));
+        static const bool debug_sync = getenv("SMAPB_DEBUG_SYNC") != nullptr;
+        if (debug_sync) CK(cudaStreamSynchronize(st));
     }
     return 0;
 }

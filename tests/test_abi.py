@@ -27,6 +27,18 @@ def test_library_exports_every_declared_symbol():
     assert lib.smapb_version() >= 100
 
 
+def test_debug_header_symbols_are_exported_too():
+    from smap_b200 import _lib
+
+    src = open(os.path.join(ROOT, "include", "smap_b200_debug.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    syms = sorted(set(re.findall(r"\b(smapb_debug_[a-z0-9_]+)\s*\(", src)))
+    assert syms == ["smapb_debug_checksums", "smapb_debug_dump"]
+    lib = _lib.load()
+    for s in syms:
+        assert hasattr(lib, s), "missing export: " + s
+
+
 def test_record_layout_matches_header():
     from smap_b200 import _lib, engine
 
