@@ -495,6 +495,13 @@ __global__ void __launch_bounds__(384, 1) conv_tc_kernel(const __grid_constant__
                 uint32_t acc_r[32];
                 tmem_ld32(taddr + (uint32_t)c0, acc_r);
                 // epilogue inputs arrive through the residual ring in the order [residual][post1][post2]
+                auto ring_release = [&](int rslot) {
+                    // The slot is refilled by TMA (async proxy) while these were generic-proxy reads: without a proxy
+                    // fence the refill is not ordered after loads that are still in flight, and under memory pressure it
+                    // did overtake them (one 16-byte unit of a row came back holding the NEXT chunk's residual).
+                    fence_proxy_async();
+                    mbar_arrive(&rempty_bar[rslot]);
+                };
                 auto ring_fetch = [&](uint4(&hh)[4], uint4(&ll)[4]) {
                     const int m = rcnt++;  // this group's FIFO position (mirrors the producer's cnt[g])
                     const int rslot = g * Cfg::SPG + (m % Cfg::SPG);
@@ -505,11 +512,9 @@ __global__ void __launch_bounds__(384, 1) conv_tc_kernel(const __grid_constant__
                         hh[j] = lds_v4(rb + sw64_off(row, j));
                         ll[j] = (NTERMS == 3) ? lds_v4(rb + Cfg::CHUNK_BYTES + sw64_off(row, j)) : make_uint4(0, 0, 0, 0);
                     }
-                    // The slot is refilled by TMA (async proxy) while these were generic-proxy reads: without a proxy
-                    // fence the refill is not ordered after loads that are still in flight, and under memory pressure it
-                    // did overtake them (one 16-byte unit of a row came back holding the NEXT chunk's residual).
-                    fence_proxy_async();
-                    mbar_arrive(&rempty_bar[rslot]);
+                    // released right away: handing the slot back only after the values are consumed (when the fence has
+                    // nothing left to wait for) measured 1.5 % slower - the refill's head start matters more
+                    ring_release(rslot);
                 };
                 auto add_planes = [&](float(&vv)[32], const uint4(&hh)[4], const uint4(&ll)[4]) {
 #pragma unroll
