@@ -100,3 +100,22 @@ def test_restated_save_result_is_pinned_to_the_reference():
 
 def test_result_file_name():
     assert result_file_name("/o", suffix="x") == "/o/stage3_root2_run_inference_test_x.json"
+
+
+def test_random_bit_patterns_print_like_python(tmp_path):
+    """Shortest round-trip digits + CPython's layout rule over the whole double / float range (incl. subnormals, huge and
+    tiny exponents, NaN and infinities): 60 k random bit patterns."""
+    rng = np.random.default_rng(12345)
+    rec = np.zeros(4, RECORD_DTYPE)
+    rec["count"] = 127
+    rec["pred3d"] = rng.integers(0, 2 ** 64, rec["pred3d"].shape, dtype=np.uint64).view(np.float64)
+    rec["pred2d"] = rng.integers(0, 2 ** 32, rec["pred2d"].shape, dtype=np.uint64).astype(np.uint32).view(np.float32)
+    rec["root_depth"] = rng.integers(0, 2 ** 64, rec["root_depth"].shape, dtype=np.uint64).view(np.float64)
+    # values near the exponent-format thresholds and round numbers
+    edge = np.array([10.0 ** k for k in range(-8, 24)] + [9.5 * 10.0 ** k for k in range(-8, 20)], np.float64)
+    rec["pred3d"][0, 0].reshape(-1)[:] = np.resize(edge, 60)
+    paths = ["p%d.jpg" % i for i in range(4)]
+    out = os.path.join(tmp_path, "rnd.json")
+    with ResultWriter(out, "CMU") as w:
+        w.append(rec, paths)
+    assert open(out).read() == python_json(rec, paths, "CMU")
