@@ -17,6 +17,12 @@ int smapb_debug_checksums(smapb_handle* h, int B, unsigned long long* sums, int 
 /* Raw copy (both bf16 planes, or fp32 for head outputs) of op `idx`'s output into host memory; returns the bytes copied. */
 long long smapb_debug_dump(smapb_handle* h, int B, int idx, void* host, long long max_bytes, int which);
 
+/* Host-only: the resampling plan smapb_preprocess uses for a src_w x src_h image (no GPU work).  dims6 = {dst_w, dst_h,
+ * pad_left, pad_top, mode (0 fixed-point bilinear, 1 exact 1/2 scale = 2x2 rounded mean, 2 copy), 0}; the tables (may be
+ * NULL) must hold dst_w, 2*dst_w, 2*dst_h and 2*dst_h entries (dst <= net size). */
+int smapb_debug_resize_plan(int src_w, int src_h, int net_w, int net_h, int* dims6, double* scale, int* xofs, short* xcoef,
+                            int* yofs, short* ycoef);
+
 /* Environment switches read when a handle / plan is built (never on the per-call path):
  *   SMAPB_DEBUG_STOP=n        run only the first n ops of the plan
  *   SMAPB_DEBUG_SYNC=1        synchronise the stream after every launch

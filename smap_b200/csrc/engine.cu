@@ -1458,6 +1458,21 @@ int smapb_preprocess_host(smapb_handle* h, const uint8_t* bgr_host, int img_h, i
     return smapb_preprocess(h, h->pre_stage, img_h, img_w, out_nchw_dev, scale_row_host, stream);
 }
 
+// host-only introspection of the resampling plan (tests compare it with the oracle over many geometries without a GPU)
+int smapb_debug_resize_plan(int src_w, int src_h, int net_w, int net_h, int* dims6, double* scale, int* xofs, short* xcoef,
+                            int* yofs, short* ycoef) {
+    if (src_w < 2 || src_h < 2 || net_w < 1 || net_h < 1 || !dims6) return -1;
+    ResizePlan P;
+    make_resize_plan(src_w, src_h, net_w, net_h, &P);
+    dims6[0] = P.dst_w, dims6[1] = P.dst_h, dims6[2] = P.pad_l, dims6[3] = P.pad_t, dims6[4] = P.mode, dims6[5] = 0;
+    if (scale) *scale = P.scale;
+    if (xofs) memcpy(xofs, P.xofs.data(), P.xofs.size() * sizeof(int));
+    if (xcoef) memcpy(xcoef, P.xcoef.data(), P.xcoef.size() * sizeof(short));
+    if (yofs) memcpy(yofs, P.yofs.data(), P.yofs.size() * sizeof(int));
+    if (ycoef) memcpy(ycoef, P.ycoef.data(), P.ycoef.size() * sizeof(short));
+    return 0;
+}
+
 // ---- RefineNet ---------------------------------------------------------------------------------
 int smapb_refine_load_weight(smapb_handle* h, const char* key, const float* host, const int64_t* shape, int ndim) {
     if (!h || !key || !host) return -1;

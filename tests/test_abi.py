@@ -33,7 +33,7 @@ def test_debug_header_symbols_are_exported_too():
     src = open(os.path.join(ROOT, "include", "smap_b200_debug.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     syms = sorted(set(re.findall(r"\b(smapb_debug_[a-z0-9_]+)\s*\(", src)))
-    assert syms == ["smapb_debug_checksums", "smapb_debug_dump"]
+    assert syms == ["smapb_debug_checksums", "smapb_debug_dump", "smapb_debug_resize_plan"]
     lib = _lib.load()
     for s in syms:
         assert hasattr(lib, s), "missing export: " + s
