@@ -12,7 +12,8 @@ B frames and the per-image skeleton records are exchanged with ONE NCCL all-gath
   e2e   : frames/s through the C-ABI call with HOST buffers (smapb_infer_host: H2D of the frames from pinned
           memory, the whole path, D2H of the skeleton records) + all-gather
   roofline : the tensor-core convolution kernel (conv_tc_kernel, the dominant kernel): algorithmic conv FLOPs of
-          one step / summed CUDA-event time of its launches, against MEASURED_PEAKS.json bf16_tflops_sustained.
+          one step / (its share of the step, from per-launch CUDA events, x the timed ms_per_step), against
+          MEASURED_PEAKS.json bf16_tflops_sustained.
           In bf16x3 mode every algorithmic FLOP is issued as 3 tensor-core FLOPs, so the tensor pipe runs at
           3 x frac of the bf16 peak.
   cpu_baseline : the CPU oracle of the same path (oracle/: PyTorch fp32 backbone on all cores + C++ association
@@ -141,46 +142,67 @@ def pick_threads():
     return best_t
 
 
-def cpu_oracle_fps(frames, threads=None, seed=1, budget_s=None):
-    """Whole path on the host: oracle backbone (torch fp32) + C++ association + numpy lift.  Runs `frames` frames, or
-    fewer (at least one) when `budget_s` seconds are used up.  -> (fps, seconds, threads, persons, frames_done)"""
-    import torch
+class CpuOracle:
+    """Whole path on the host: oracle backbone (torch fp32, all host threads) + C++ association (single thread, as the
+    reference's is: its OpenMP pragmas are commented out, extensions/association.cpp:79,100) + numpy lift.  Weights, the
+    association library and the scale record are set up ONCE (outside every timed region)."""
 
-    from oracle import assoc, lift_numpy, smap_torch
+    def __init__(self, threads=None):
+        import torch
 
-    # host cores (torchrun exports OMP_NUM_THREADS=1, which would starve the CPU baseline)
-    torch.set_num_threads(threads or pick_threads())
-    sd = smap_torch.make_state_dict(0, "identity")
-    x = smap_torch.make_input(frames, IN_H, IN_W, seed=seed)
-    scale = lift_numpy.default_scale(1920, 1080)
-    assoc.lib()
-    t0 = time.perf_counter()
-    persons = 0
-    done = 0
-    for i in range(frames):
-        hm, dd, rd = smap_torch.smap_forward(sd, x[i:i + 1])
-        smap_torch.rescale_reference_cuda(hm)
-        bodies = assoc.connect(hm[0].numpy(), rd[0, 0].numpy())
-        p2, p3, rdep = lift_numpy.lift(bodies, dd[0].numpy(), rd[0, 0].numpy(), scale)
-        persons += len(p2)
-        done += 1
-        if budget_s is not None and time.perf_counter() - t0 >= budget_s:
-            break
-    dt = time.perf_counter() - t0
-    return done / dt, dt, torch.get_num_threads(), persons, done
+        from oracle import assoc, lift_numpy, smap_torch
+
+        self.torch, self.assoc, self.lift_numpy, self.smap_torch = torch, assoc, lift_numpy, smap_torch
+        # host cores (torchrun exports OMP_NUM_THREADS=1, which would starve the CPU baseline)
+        torch.set_num_threads(threads or pick_threads())
+        self.threads = torch.get_num_threads()
+        self.sd = smap_torch.make_state_dict(0, "identity")
+        self.scale = lift_numpy.default_scale(1920, 1080)
+        assoc.lib()
+
+    def make_frames(self, n, seed=1):
+        return self.smap_torch.make_input(n, IN_H, IN_W, seed=seed)
+
+    def run(self, x, budget_s=None):
+        """-> (seconds, frames_done, persons): the frames of x one by one, stopping early (after at least one) when
+        budget_s seconds are used up."""
+        t0 = time.perf_counter()
+        persons = done = 0
+        for i in range(x.shape[0]):
+            hm, dd, rd = self.smap_torch.smap_forward(self.sd, x[i:i + 1])
+            self.smap_torch.rescale_reference_cuda(hm)
+            bodies = self.assoc.connect(hm[0].numpy(), rd[0, 0].numpy())
+            p2, p3, rdep = self.lift_numpy.lift(bodies, dd[0].numpy(), rd[0, 0].numpy(), self.scale)
+            persons += len(p2)
+            done += 1
+            if budget_s is not None and time.perf_counter() - t0 >= budget_s:
+                break
+        return time.perf_counter() - t0, done, persons
+
+
+def ref_gpu_path_note():
+    """The reference's own single-GPU path (eager PyTorch/cuDNN backbone + unmodified dapalib per image + numpy lift) is
+    measured builder-side by tests/ref_gpu_fps.py on the same kind of box; bench.py only quotes the committed number."""
+    p = os.path.join(ROOT, "profiles", "r02_reference_gpu_path.json")
+    if os.path.exists(p):
+        return json.load(open(p))
+    return None
 
 
 def run_reference(args):
+    """Reference arm: the CPU port of the whole path (oracle/) on the box's host cores; each step = a bounded sample of
+    the workload (1 frame of the 8-frame batch).  Only the per-frame work is inside the timed region."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     frames_per_step = 1
-    for _ in range(max(1, min(args.warmup, 1))):
-        cpu_oracle_fps(1)
+    oracle = CpuOracle()
+    xs = [oracle.make_frames(frames_per_step, seed=1 + s) for s in range(args.warmup + args.steps)]
+    for s in range(args.warmup):
+        oracle.run(xs[s])
     t0 = time.perf_counter()
-    threads = None
     for s in range(args.steps):
-        fps, dt, threads, _, _ = cpu_oracle_fps(frames_per_step, seed=1 + s)
+        oracle.run(xs[args.warmup + s])
     total = time.perf_counter() - t0
     value = args.steps * frames_per_step / total
     line = {
@@ -188,11 +210,17 @@ def run_reference(args):
         "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "fp32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "frames_per_step": frames_per_step},
-        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": threads, "kind": "port",
-                         "sample": "%d frame(s) per step x %d steps, whole path on host cores" % (frames_per_step, args.steps)},
+        "config": {"workload": WORKLOAD, "frames_per_step": frames_per_step,
+                   "arm": "cpu port of the reference path (oracle/); the reference has no GPU-free association of its own "
+                          "and /root/reference does not travel to the GPU box"},
+        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": oracle.threads, "kind": "port",
+                         "sample": "%d frame(s) per step x %d steps, whole path on host cores; weights/input/library set up "
+                                   "outside the timed region" % (frames_per_step, args.steps)},
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
+    g = ref_gpu_path_note()
+    if g:
+        line["reference_gpu_path"] = g
     print(json.dumps(line))
 
 
@@ -209,18 +237,26 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.init_process_group("nccl", device_id=dev)
     B = args.batch
     sd0 = schema.make_state_dict(0, "identity")
+    NE = max(1, args.engines)
+    # one handle per batch in flight; every handle issues on its OWN non-blocking stream (nothing in the timed loops
+    # touches the legacy default stream) and owns its NCCL communicator, so the per-step all-gather is ordered only
+    # against the batch it belongs to
     engines = []
-    for _ in range(max(1, args.engines)):
-        e = Engine(local, max_batch=B, in_h=IN_H, in_w=IN_W)
+    for _ in range(NE):
+        e = Engine(local, max_batch=B, in_h=IN_H, in_w=IN_W, stream=torch.cuda.Stream(dev))
         e.load_state_dict(sd0, precision=args.precision)
         engines.append(e)
+    gather = world > 1
+    if gather:
+        for e in engines:
+            e.init_comm()
     eng = engines[0]
-    NE = len(engines)
-    dev = torch.device("cuda", local)
+    cur = torch.cuda.current_stream()
 
     # inputs: NROT distinct batches so that consecutive steps never re-read the same frames from L2
     NROT = 4
@@ -230,41 +266,63 @@ def run_ours(args):
               f_y=1920.0, cx=960.0, cy=540.0)
     scales_host = torch.from_numpy(np.stack([scale_row(sc)] * B)).pin_memory()
     scales_dev = scales_host.to(dev)
-    host_out = torch.empty(B, RECORD_BYTES, dtype=torch.uint8).pin_memory()
+    NOUT = B * (world if gather else 1)
+    dev_outs = [torch.empty(NOUT, RECORD_BYTES, dtype=torch.uint8, device=dev) for _ in range(NE)]
+    torch.cuda.synchronize()
+    if gather:
+        # tile shapes: the committed table covers this workload; anything it does not cover is tuned by rank 0 only
+        if rank == 0:
+            eng.infer_device(dev_batches[0], scales_dev, out=torch.empty(B, RECORD_BYTES, dtype=torch.uint8, device=dev))
+            torch.cuda.synchronize()
+        dist.barrier()
+        sdist.sync_tile_table()
 
     def step_device(i):
-        rec = engines[i % NE].infer_device(dev_batches[i % NROT], scales_dev, do_flip=bool(args.flip))
-        return sdist.allgather_records(rec)  # one NCCL all-gather of the skeleton records (no-op at world 1)
+        # whole path + ONE ncclAllGather of the skeleton records (world > 1), all on the handle's stream / in its graph
+        engines[i % NE].infer_device(dev_batches[i % NROT], scales_dev, do_flip=bool(args.flip), out=dev_outs[i % NE],
+                                     gather=gather)
 
-    DEPTH = 2 * NE  # batches in flight: two slots per handle
-    host_outs = [torch.empty(B, RECORD_BYTES, dtype=torch.uint8).pin_memory() for _ in range(DEPTH)]
+    DEPTH = 2 * NE  # batches in flight on the host path: two slots per handle
+    host_outs = [torch.empty(NOUT, RECORD_BYTES, dtype=torch.uint8).pin_memory() for _ in range(DEPTH)]
 
     def finish_host(j):
-        engines[j % NE].wait((j // NE) % 2)  # step j's records are in host memory
-        if world > 1:
-            sdist.allgather_records(host_outs[j % DEPTH].to(dev, non_blocking=True))
+        engines[j % NE].wait((j // NE) % 2)  # step j's (gathered) records are in host memory
 
     def step_host(i, last=False):
         # pipeline through the C ABI (two slots per handle): the H2D of step i overlaps the compute of earlier steps;
-        # every step still performs its own H2D (pinned frames) and D2H (records) inside the timed region
+        # every step still performs its own H2D (pinned frames) and D2H (records) inside the timed region.  With
+        # world > 1 the records are all-gathered on the device before the single D2H.
         if i >= DEPTH:
             finish_host(i - DEPTH)
         engines[i % NE].submit_host((i // NE) % 2, host_batches[i % NROT], scales_host, host_outs[i % DEPTH],
-                                    do_flip=bool(args.flip))
+                                    do_flip=bool(args.flip), gather=gather)
         if last:
             for j in range(max(0, i - DEPTH + 1), i + 1):
                 finish_host(j)
 
+    def run_device(steps):
+        for i in range(steps):
+            step_device(i)
+
+    def run_host(steps):
+        for i in range(steps):
+            step_host(i, last=(i == steps - 1))
+
     def timed(fn, steps):
+        """CUDA events bracketing every stream the step uses: e0 on the current stream, every handle stream waits for it;
+        every handle stream is joined back before e1.  Barrier + synchronize on both sides, max over ranks."""
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
-        e0.record()
-        for i in range(steps):
-            fn(i)
-        e1.record()
+        e0.record(cur)
+        for e in engines:
+            e.stream.wait_event(e0)
+        fn(steps)
+        for e in engines:
+            cur.wait_stream(e.stream)
+        e1.record(cur)
         torch.cuda.synchronize()
         wall = time.perf_counter() - t0
         ms = e0.elapsed_time(e1)
@@ -275,41 +333,43 @@ def run_ours(args):
             dist.barrier()
         return ms, wall
 
-    # every (handle, input batch) pair must have gone through its eager runs and graph capture before timing
-    n_warm = max(3, args.warmup, 3 * NE * NROT // math.gcd(NE, NROT) if NE > 1 else 3 * NROT)
-    for i in range(n_warm):
-        step_device(i)
+    # SETUP (not warm-up, not timed): every (handle, input batch) pair the loops will use goes through its two eager
+    # runs (lazy allocations, NCCL connections) and its CUDA-graph capture.  Then exactly --warmup untimed steps.
+    n_setup = 3 * NE * NROT // math.gcd(NE, NROT)
+    run_device(n_setup)
     torch.cuda.synchronize()
     if args.ncu_one_step:
         torch.cuda.profiler.start()
         step_device(0)
         torch.cuda.synchronize()
         torch.cuda.profiler.stop()
-        eng.close()
+        for e in engines:
+            e.close()
         return
+    run_device(args.warmup)
+    torch.cuda.synchronize()
 
     sampler = ClockSampler(local)
     sampler.start()
     l0 = sum(e.launch_count() for e in engines)
-    ms_dev, wall_dev = timed(step_device, args.steps)
+    ms_dev, wall_dev = timed(run_device, args.steps)
     launches = sum(e.launch_count() for e in engines) - l0
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
-    for i in range(DEPTH):
-        step_host(i, last=(i == DEPTH - 1))
-
-    def run_host(i):
-        step_host(i, last=(i == args.steps - 1))
-
+    run_host(max(DEPTH, args.warmup))  # slot buffers + graphs for the slot pointers, then the host warm-up
+    torch.cuda.synchronize()
     ms_host, wall_host = timed(run_host, args.steps)
 
-    # roofline leg: per-kernel CUDA-event timing of the same step (events on the launching stream)
+    # roofline leg: per-kernel CUDA events on the launching stream (one handle, eager, every launch bracketed) give each
+    # kernel's SHARE of the serialised step; the headline mode (graph replay, NE handles overlapping) cannot be
+    # event-bracketed per kernel, so the kernel time in that mode is share x the timed ms_per_step.
     n_conv, conv_flops = eng.plan_info(B)
     prof_steps = min(args.steps, 5)
+    prof_out = torch.empty(B, RECORD_BYTES, dtype=torch.uint8, device=dev)
     eng.profile_begin()
     for i in range(prof_steps):
-        eng.infer_device(dev_batches[i % NROT], scales_dev, do_flip=bool(args.flip))
+        eng.infer_device(dev_batches[i % NROT], scales_dev, do_flip=bool(args.flip), out=prof_out)
     prof = eng.profile_end(args.profile_csv or None)
     torch.cuda.synchronize()
 
@@ -318,29 +378,42 @@ def run_ours(args):
         frames = world * B * args.steps
         value = frames / (ms_dev * 1e-3)
         e2e = frames / (wall_host)
+        ms_per_step = ms_dev / args.steps
         conv_ms, conv_n = prof["conv"]
         fwd = 2 if args.flip else 1
-        conv_ms_per_step = conv_ms / prof_steps
-        achieved = conv_flops * fwd / (conv_ms_per_step * 1e-3) * 1e-12 if conv_ms_per_step > 0 else 0.0
         total_prof_ms = sum(v[0] for v in prof.values()) / prof_steps
+        conv_ms_serial = conv_ms / prof_steps
+        share = conv_ms_serial / total_prof_ms
+        conv_ms_per_step = share * ms_per_step  # in the timed (graph, NE handles) mode
+        achieved = conv_flops * fwd / (conv_ms_per_step * 1e-3) * 1e-12 if conv_ms_per_step > 0 else 0.0
         traffic, traffic_src = None, None
-        tp = os.path.join(ROOT, "profiles", "r01_conv_traffic.json")
-        if os.path.exists(tp):  # committed ncu capture of the same command (tools/gpu_profile.sh)
-            tj = json.load(open(tp))
-            traffic, traffic_src = tj["mean_dram_bytes_per_launch"], "profiles/r01_conv_traffic.json"
+        for name in ("r02_conv_traffic.json", "r01_conv_traffic.json"):
+            tp = os.path.join(ROOT, "profiles", name)
+            if os.path.exists(tp):  # committed ncu capture of the same command (tools/gpu_profile.sh)
+                tj = json.load(open(tp))
+                traffic, traffic_src = tj["mean_dram_bytes_per_launch"], "profiles/" + name
+                break
+        # association (nms + paf + group) against the HBM roofline: algorithmic bytes per frame = heat-maps
+        # read once 43*128*208*4 + root-depth map 128*208*4 + skeleton records written
+        assoc_ms = prof["assoc"][0] / prof_steps
+        assoc_bytes = B * (43 * 128 * 208 * 4 + 128 * 208 * 4 + 127 * 15 * 4 * 4)
+        assoc_gbs = assoc_bytes / (assoc_ms * 1e-3) * 1e-9 if assoc_ms > 0 else 0.0
         line = {
             "metric": "end-to-end FPS @832x512 (backbone+association+lift)", "value": value, "unit": "frames/s",
-            "n_gpus": world, "steps": args.steps, "warmup": n_warm, "ms_per_step": ms_dev / args.steps,
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16x3 (split-bf16 operands, fp32 accumulate; fp32-faithful)" if args.precision == "bf16x3" else "bf16",
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "frames_per_gpu_per_step": B, "flip_tta": int(args.flip),
                        "l2": "inputs rotate over %d distinct batches (%.0f MB) and every step streams >2 GB of activations (> 126 MB L2)"
                              % (NROT, NROT * B * 3 * IN_H * IN_W * 4 / 1e6),
-                       "parallelism": "dp%d, one all-gather of skeleton records per step" % world,
-                       "batches_in_flight_per_gpu": NE},
+                       "parallelism": "dp%d, one ncclAllGather of skeleton records per step on the compute stream (inside the CUDA graph)" % world,
+                       "batches_in_flight_per_gpu": NE,
+                       "setup_steps_before_warmup": n_setup,
+                       "setup": "graph capture per (handle, input batch) pair; not warm-up, not timed"},
             "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": B * 3 * IN_H * IN_W * 4 + B * 9 * 8,
-                    "d2h_bytes_per_step": B * RECORD_BYTES, "ms_per_step": 1e3 * wall_host / args.steps},
+                    "d2h_bytes_per_step": NOUT * RECORD_BYTES, "ms_per_step": 1e3 * wall_host / args.steps,
+                    "batches_in_flight_per_gpu": DEPTH},
             "gpu_launches": int(launches),
             "clocks": sampler.result(),
             "roofline": {"bound": "tensor", "kernel": "conv_tc_kernel (%d launches/step)" % (conv_n // prof_steps),
@@ -348,23 +421,36 @@ def run_ours(args):
                          "peak_source": peak_src + " bf16_tflops_sustained",
                          "algorithmic_gflop_per_step": conv_flops * fwd * 1e-9,
                          "tensor_pipe_flop_multiplier": 3 if args.precision == "bf16x3" else 1,
-                         "kernel_ms_per_step": conv_ms_per_step, "share_of_step": conv_ms_per_step / total_prof_ms,
+                         "kernel_ms_per_step": conv_ms_per_step, "share_of_step": share,
+                         "how": "share (per-launch CUDA events, one handle, eager) x timed ms_per_step (graph replay, %d handles)" % NE,
+                         "kernel_ms_per_step_serialised_eager": conv_ms_serial,
                          "traffic": traffic, "traffic_unit": "bytes per launch (dram read+write, ncu)",
                          "traffic_source": traffic_src},
+            "roofline_assoc": {"bound": "hbm", "kernel": "nms_kernel + paf_kernel + group_kernel",
+                               "achieved": assoc_gbs, "peak": peak_bw, "unit": "GB/s", "frac": assoc_gbs / peak_bw,
+                               "algorithmic_bytes_per_step": assoc_bytes, "kernel_ms_per_step": assoc_ms,
+                               "note": "batch 8: 3 launches of 120 / 112 / 8 CTAs - latency bound, not bandwidth bound; the "
+                                       "B=64 ncu capture in profiles/ is the bandwidth number"},
             "breakdown_ms_per_step": {k: v[0] / prof_steps for k, v in prof.items() if v[1]},
         }
+        g = ref_gpu_path_note()
+        if g:
+            line["reference_gpu_path"] = dict(g, ratio_value=value / g["value"] if g.get("value") else None)
         if not args.no_cpu_baseline:
-            fps, dt, threads, persons, nfr = cpu_oracle_fps(8, budget_s=20.0)
-            line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
+            oracle = CpuOracle()
+            x = oracle.make_frames(8)
+            dt, nfr, persons = oracle.run(x, budget_s=20.0)
+            line["cpu_baseline"] = {"value": nfr / dt, "unit": "frames/s", "cores": oracle.threads, "kind": "port",
                                     "sample": "%d frames of the same workload (bounded to ~20 s), whole path (oracle/: torch fp32 "
                                               "backbone on %d threads + single-thread C++ association + numpy lift), %.1f s"
-                                              % (nfr, threads, dt)}
+                                              % (nfr, oracle.threads, dt)}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
-        dist.destroy_process_group()
     for e in engines:
         e.close()
+    if world > 1:
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -126,6 +126,33 @@ int smapb_submit_host(smapb_handle* h, int slot, const float* imgs_nchw_host, co
                       smapb_record* records_host);
 int smapb_wait(smapb_handle* h, int slot);
 
+/* ---- multi-GPU: frames are sharded over ranks, ONE exchange step per batch --------------------------------------- */
+/* The reference's inference path is single-GPU (exps/stage3_root2/test.py:198 calls get_test_loader with num_gpu=1);
+ * its data loader's rank split (lib/utils/dataloader.py:80-85: contiguous blocks of frames per rank) is the sharding
+ * rule used here, and the only exchange is one ncclAllGather of the fixed-stride smapb_record[B] per batch
+ * (SURVEY.md 8(e)).  NCCL is bound at run time (dlopen of libnccl.so.2 - inside a PyTorch process that is the instance
+ * torch loaded), so the library has no link-time dependency on it and a communicator may come from either side:
+ *   smapb_comm_unique_id + smapb_comm_create : the handle creates (and owns) its communicator; rank 0 makes the
+ *       128-byte ncclUniqueId, the host side distributes it (any transport), every rank calls smapb_comm_create.
+ *   smapb_comm_attach : borrow an existing ncclComm_t (e.g. torch.distributed's ProcessGroupNCCL._comm_ptr()).
+ * One communicator per handle: two handles of a rank keep two batches in flight without ordering constraints
+ * between their collectives. */
+int smapb_comm_unique_id(void* id128 /* out: 128 bytes */);
+int smapb_comm_create(smapb_handle* h, const void* id128, int rank, int world);
+int smapb_comm_attach(smapb_handle* h, void* nccl_comm /* ncclComm_t, caller-owned */, int rank, int world);
+/* The exchange step by itself: all-gather B records per rank into all_records_dev[world * B] (rank order), on `stream`.
+ * nccl_comm NULL = the handle's communicator. */
+int smapb_allgather_records(smapb_handle* h, void* nccl_comm, const smapb_record* records_dev, smapb_record* all_records_dev,
+                            int B, void* stream);
+/* smapb_infer_device / smapb_submit_host followed by the all-gather on the SAME stream, inside the same CUDA graph
+ * (set SMAPB_NCCL_EAGER=1 to keep the collective outside the graph, still stream-ordered): all_records receives
+ * world * B records in rank order - the frames of the global batch in their original order.  The host variant gathers
+ * on the device (NVLink) and then performs a single D2H of the gathered records. */
+int smapb_infer_device_gather(smapb_handle* h, const float* imgs_nchw_dev, const double* scales_dev, int B, int do_flip,
+                              smapb_record* all_records_dev, void* stream);
+int smapb_submit_host_gather(smapb_handle* h, int slot, const float* imgs_nchw_host, const double* scales_host, int B,
+                             int do_flip, smapb_record* all_records_host);
+
 /* ---- RefineNet post-processing (optional; the reference enables it with `-rp`, exps/stage3_root2/test.sh) ------- */
 /* Replaces: refine_model.load_state_dict(torch.load(path)) (exps/stage3_root2/test.py:213-214) for model/refinenet.py:
  * keys "block.layer{1..4}.0.{weight,bias}" (Linear), "block.layer{1..4}.1.{weight,bias,running_mean,running_var}"
@@ -167,6 +194,13 @@ int64_t smapb_launch_count(const smapb_handle* h);
  * 6-element arrays and, if csv_path is not NULL, writes one line per launch. */
 int smapb_profile_begin(smapb_handle* h);
 int smapb_profile_end(smapb_handle* h, double* ms_by_kind, int* launches_by_kind, const char* csv_path);
+/* Tile shapes of the tensor-core convolutions (process-wide): one line per layer geometry, "key<TAB>BLOCK_N<TAB>cta_group".
+ * Geometries found in the table use its entry; others are autotuned once per process (SMAPB_NO_AUTOTUNE=1: cost model)
+ * and added to it.  Loading the same table in every process makes tile selection - and with it every result bit -
+ * independent of the handle, the process and the rank.  smapb_get_tile_table returns the bytes needed (incl. the
+ * terminating 0) and fills buf up to cap. */
+int smapb_set_tile_table(const char* text);
+int smapb_get_tile_table(char* buf, int cap);
 /* conv plan: number of tensor-core conv launches per forward and their algorithmic FLOPs (2*MACs, 1x) */
 int smapb_plan_info(const smapb_handle* h, int B, int* n_conv_launches, double* conv_flops);
 /* Run one standalone convolution through the tensor-core path (test/bench hook).

@@ -7,7 +7,7 @@ functional graph walker, not as a module tree, so it shares no structure with
 model/smap.py; parity with the real reference module is pinned by
 tests/golden/make_golden.py (which imports /root/reference/model/smap.py in the
 build container, runs it on seeded inputs and commits the outputs) and
-tests/test_oracle_backbone.py.
+tests/test_oracle_golden.py.
 
 Also restates the reference's random initialisation (model/smap.py:111-117 +
 PyTorch defaults for every other conv) with an explicit generator so that
@@ -16,8 +16,8 @@ PyTorch defaults for every other conv) with an explicit generator so that
 import torch
 import torch.nn.functional as F
 
-from smap_b200.schema import (BN_EPS, LAYERS, PLANES, UP_IN, make_input, make_state_dict,  # noqa: F401
-                               unit_specs)
+from .schema_ref import (BN_EPS, LAYERS, PLANES, UP_IN, make_input, make_state_dict,  # noqa: F401
+                         unit_specs)
 
 
 # ----------------------------------------------------------------------------

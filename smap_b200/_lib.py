@@ -16,6 +16,8 @@ EXPORTS = [
     "smapb_plan_info", "smapb_conv_test", "smapb_profile_begin", "smapb_profile_end", "smapb_submit_host", "smapb_wait",
     "smapb_refine_load_weight", "smapb_refine_finalize", "smapb_refine_mlp", "smapb_refine3d", "smapb_set_refine",
     "smapb_json_open", "smapb_json_append", "smapb_json_close", "smapb_preprocess", "smapb_preprocess_host",
+    "smapb_comm_unique_id", "smapb_comm_create", "smapb_comm_attach", "smapb_allgather_records",
+    "smapb_infer_device_gather", "smapb_submit_host_gather", "smapb_set_tile_table", "smapb_get_tile_table",
 ]
 
 _lib = None
@@ -69,6 +71,14 @@ def load():
     lib.smapb_set_refine.argtypes = [vp, i32]
     lib.smapb_preprocess.argtypes = [vp, vp, i32, i32, vp, c.POINTER(c.c_double), vp]
     lib.smapb_preprocess_host.argtypes = [vp, vp, i32, i32, vp, c.POINTER(c.c_double), vp]
+    lib.smapb_comm_unique_id.argtypes = [vp]
+    lib.smapb_comm_create.argtypes = [vp, vp, i32, i32]
+    lib.smapb_comm_attach.argtypes = [vp, vp, i32, i32]
+    lib.smapb_allgather_records.argtypes = [vp, vp, vp, vp, i32, vp]
+    lib.smapb_infer_device_gather.argtypes = [vp, vp, vp, i32, i32, vp, vp]
+    lib.smapb_submit_host_gather.argtypes = [vp, i32, vp, vp, i32, i32, vp]
+    lib.smapb_set_tile_table.argtypes = [c.c_char_p]
+    lib.smapb_get_tile_table.argtypes = [c.c_char_p, i32]
     lib.smapb_json_open.argtypes = [c.POINTER(vp), c.c_char_p, c.c_char_p]
     lib.smapb_json_append.argtypes = [vp, vp, i32, c.POINTER(c.c_char_p)]
     lib.smapb_json_close.argtypes = [vp]

@@ -22,7 +22,10 @@ __constant__ float c_bone_length[NL] = {26.42178982f, 48.36980909f, 14.88291009f
                                         39.03553194f, 12.4644364f, 48.19076948f, 39.03553252f};
 
 // ---------------------------------------------------------------------------------------------
-// plane staging: one elected thread issues chunked bulk copies, everyone waits on the mbarrier.
+// plane staging: warp 0 issues the bulk copies (one 16 KB chunk per lane per round, so up to 32 copies are in
+// flight per CTA) and is the ONLY warp that polls the mbarrier; everyone else parks on the CTA barrier.  (Round 1
+// had one thread issue 32 KB chunks while all 1024 threads spun on mbarrier.try_wait: the polling traffic slowed the
+// very shared-memory writes it was waiting for - 15 GB/s per SM.)
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void stage_planes(float* dst, const float* src, uint32_t bytes, uint64_t* bar) {
     if (threadIdx.x == 0) {
@@ -30,59 +33,87 @@ __device__ __forceinline__ void stage_planes(float* dst, const float* src, uint3
         fence_mbar_init();
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        mbar_arrive_expect_tx(bar, bytes);
-        const uint32_t CH = 32768;
-        for (uint32_t off = 0; off < bytes; off += CH) {
+    if (threadIdx.x < 32) {
+        if (threadIdx.x == 0) mbar_arrive_expect_tx(bar, bytes);
+        __syncwarp();
+        const uint32_t CH = 16384;
+        for (uint32_t off = threadIdx.x * CH; off < bytes; off += 32 * CH) {
             const uint32_t n = bytes - off < CH ? bytes - off : CH;
             bulk_g2s((char*)dst + off, (const char*)src + off, n, bar);
         }
+        mbar_wait(bar, 0);
     }
-    mbar_wait(bar, 0);
+    __syncthreads();
+}
+
+// ---- thread-block-cluster helpers (NMS row bands exchange their peak counts through distributed shared memory) ----
+__device__ __forceinline__ uint32_t cl_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cl_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ int cl_ld_s32(const int* local, uint32_t rank) {
+    uint32_t a;
+    int v;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(a) : "r"(smem_u32(local)), "r"(rank));
+    asm volatile("ld.shared::cluster.s32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
 }
 
 // ---------------------------------------------------------------------------------------------
-// NMS: one CTA per (image, key-point channel).  grid (NJ, B), block NMS_THREADS.
-// Peak order is raster order (required: candidate indices are part of the parity contract), obtained
-// with warp ballots over contiguous per-warp pixel segments + one block-level scan of 32 warp totals.
+// NMS: a CLUSTER of `bands` CTAs per (image, key-point channel); CTA r owns the rows [r*rows, (r+1)*rows) of the
+// plane and stages them (+3 halo rows on each side for the 7x7 centroid) with one bulk copy - the rows are
+// contiguous in memory.  grid (bands, NJ, B), cluster (bands, 1, 1), block NMS_THREADS.
+// Peak order is raster order (required: candidate indices are part of the parity contract): warp ballots over
+// contiguous per-warp pixel segments + a block scan of the warp totals give the order inside a band, and the bands
+// exchange their totals through distributed shared memory (band r starts at the sum of bands < r).  This replaces the
+// reference's global thrust::exclusive_scan (nmsBase.cu:165-166) and works for any map size (config 5: 256x256).
 // ---------------------------------------------------------------------------------------------
-constexpr int NMS_THREADS = 1024;
+constexpr int NMS_THREADS = 256;
 constexpr int NMS_WARPS = NMS_THREADS / 32;
+constexpr int NMS_MAX_BANDS = 8;  // portable cluster size
 
-__global__ void __launch_bounds__(NMS_THREADS, 1)
-nms_kernel(const float* __restrict__ hms, int nchan, int h, int w, float thr, float* __restrict__ peaks) {
+__global__ void __launch_bounds__(NMS_THREADS)
+nms_kernel(const float* __restrict__ hms, int nchan, int h, int w, int rows, float thr, float* __restrict__ peaks) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int hw = h * w;
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
-    float* plane = reinterpret_cast<float*>(smem_raw + 16);
-    uint32_t* masks = reinterpret_cast<uint32_t*>(plane + hw);  // one ballot word per 32 pixels
-    const int nwords = (hw + 31) / 32;
-    int* warp_tot = reinterpret_cast<int*>(masks + nwords);
-
-    const int c = blockIdx.x, img = blockIdx.y;
-    const float* src = hms + ((size_t)img * nchan + c) * hw;
+    int* s_cnt = reinterpret_cast<int*>(smem_raw + 8);     // this band's peak count (read by the other bands)
+    int* warp_tot = reinterpret_cast<int*>(smem_raw + 16);  // [NMS_WARPS]
+    float* tile = reinterpret_cast<float*>(smem_raw + 64);  // staged rows [r_lo, r_hi)
+    const int band = (int)cl_rank(), bands = (int)gridDim.x;
+    const int c = blockIdx.y, img = blockIdx.z;
+    const int r0 = band * rows, r1 = min(h, r0 + rows);           // owned rows (may be empty for the last bands)
+    const int r_lo = max(0, r0 - 3), r_hi = min(h, r1 + 3);       // staged rows
+    const int n_own = max(0, r1 - r0) * w;
+    const int nwords = (n_own + 31) / 32;
+    uint32_t* masks = reinterpret_cast<uint32_t*>(tile + (size_t)(rows + 6) * w);  // one ballot word per 32 owned pixels
+    const float* src = hms + ((size_t)img * nchan + c) * h * w;
     float* out = peaks + ((size_t)img * NJ + c) * (MAXP + 1) * 3;
 
     pdl_wait();
-    stage_planes(plane, src, (uint32_t)hw * 4u, bar);
+    if (r_hi > r_lo) stage_planes(tile, src + (size_t)r_lo * w, (uint32_t)((r_hi - r_lo) * w) * 4u, bar);
+    const float* plane = tile - (size_t)r_lo * w;  // plane[y * w + x] for staged y
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // contiguous run of ballot words per warp
-    const int wpw = (nwords + NMS_WARPS - 1) / NMS_WARPS;
-    const int w0 = warp * wpw, w1 = min(nwords, w0 + wpw);
+    const int wpw = (nwords + NMS_WARPS - 1) / NMS_WARPS;  // contiguous run of ballot words per warp
+    const int w0 = min(nwords, warp * wpw), w1 = min(nwords, w0 + wpw);
+    const int base = r0 * w;
     int cnt = 0;
     for (int wi = w0; wi < w1; wi++) {
-        const int i = wi * 32 + lane;
+        const int i = base + wi * 32 + lane;
         bool f = false;
-        if (i < hw) {
+        if (wi * 32 + lane < n_own) {
             const int y = i / w, x = i - y * w;
-            if (x > 0 && x < w - 1 && y > 0 && y < h - 1) {
+            if (x > 0 && x < w - 1 && y > 0 && y < h - 1) {  // nmsBase.cu:24
                 const float v = plane[i];
                 if (v > thr) {
-                    const float* r0 = plane + i - w;
-                    const float* r2 = plane + i + w;
-                    f = v > r0[-1] && v > r0[0] && v > r0[1] && v > plane[i - 1] && v > plane[i + 1] &&
-                        v > r2[-1] && v > r2[0] && v > r2[1];
+                    const float* q0 = plane + i - w;
+                    const float* q2 = plane + i + w;
+                    f = v > q0[-1] && v > q0[0] && v > q0[1] && v > plane[i - 1] && v > plane[i + 1] &&
+                        v > q2[-1] && v > q2[0] && v > q2[1];
                 }
             }
         }
@@ -92,23 +123,32 @@ nms_kernel(const float* __restrict__ hms, int nchan, int h, int w, float thr, fl
     }
     if (lane == 0) warp_tot[warp] = cnt;
     __syncthreads();
-    // exclusive prefix over warps (32 values -> one shuffle-reduce per warp)
+    // exclusive prefix over the warps of this band
     int t = (lane < NMS_WARPS) ? warp_tot[lane] : 0;
     int before = (lane < warp) ? t : 0;
-    int total = t;
+    int band_total = t;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         before += __shfl_xor_sync(0xffffffffu, before, o);
-        total += __shfl_xor_sync(0xffffffffu, total, o);
+        band_total += __shfl_xor_sync(0xffffffffu, band_total, o);
     }
-    int running = before;
+    if (threadIdx.x == 0) *s_cnt = band_total;
+    cl_sync();  // every band's count is published
+    int band_off = 0, total = 0;
+    for (int r = 0; r < bands; r++) {
+        const int v = (r == band) ? band_total : cl_ld_s32(s_cnt, (uint32_t)r);
+        if (r < band) band_off += v;
+        total += v;
+    }
+    cl_sync();  // nobody leaves (or reuses s_cnt) while a peer may still read it
+    int running = band_off + before;
     for (int wi = w0; wi < w1; wi++) {
         const uint32_t m = masks[wi];
         if (m == 0) continue;
         if ((m >> lane) & 1u) {
             const int peakIndex = running + __popc(m & ((1u << lane) - 1u));
             if (peakIndex < MAXP) {  // nmsBase.cu:92
-                const int i = wi * 32 + lane;
+                const int i = base + wi * 32 + lane;
                 const int py = i / w, px = i - py * w;
                 float xAcc = 0.f, yAcc = 0.f, sAcc = 0.f;
                 for (int dy = -3; dy <= 3; dy++) {
@@ -117,11 +157,11 @@ nms_kernel(const float* __restrict__ hms, int nchan, int h, int w, float thr, fl
                     for (int dx = -3; dx <= 3; dx++) {
                         const int x = px + dx;
                         if (x < 0 || x >= w) continue;
-                        const float s = plane[y * w + x];
-                        if (s > 0) {
-                            xAcc = __fmaf_rn((float)x, s, xAcc);  // FFMA in the reference SASS
-                            yAcc = __fmaf_rn((float)y, s, yAcc);
-                            sAcc = __fadd_rn(sAcc, s);
+                        const float sc = plane[y * w + x];
+                        if (sc > 0) {
+                            xAcc = __fmaf_rn((float)x, sc, xAcc);  // FFMA in the reference SASS
+                            yAcc = __fmaf_rn((float)y, sc, yAcc);
+                            sAcc = __fadd_rn(sAcc, sc);
                         }
                     }
                 }
@@ -133,14 +173,16 @@ nms_kernel(const float* __restrict__ hms, int nchan, int h, int w, float thr, fl
         }
         running += __popc(m);
     }
-    const int count = total < MAXP ? total : MAXP;
-    if (threadIdx.x == 0) {
-        out[0] = (float)count;
-        out[1] = 0.f;
-        out[2] = 0.f;
+    if (band == 0) {
+        const int count = total < MAXP ? total : MAXP;
+        if (threadIdx.x == 0) {
+            out[0] = (float)count;
+            out[1] = 0.f;
+            out[2] = 0.f;
+        }
+        // deterministic tail: slots the reference leaves uninitialised are zeroed
+        for (int k = (count + 1) * 3 + threadIdx.x; k < (MAXP + 1) * 3; k += NMS_THREADS) out[k] = 0.f;
     }
-    // deterministic tail: slots the reference leaves uninitialised are zeroed
-    for (int k = (count + 1) * 3 + threadIdx.x; k < (MAXP + 1) * 3; k += NMS_THREADS) out[k] = 0.f;
     pdl_trigger();
 }
 
@@ -187,14 +229,17 @@ __device__ __forceinline__ float paf_process(float ax, float ay, float bx, float
     return -1.f;
 }
 
+// STAGED: both planes fit in shared memory (the parity configuration 128x208: 213 KB) and are staged once; otherwise
+// (larger maps, e.g. 256x256 at a 1024x1024 input) the line integrals gather straight from global memory / L2.
+template <bool STAGED>
 __global__ void __launch_bounds__(PAF_THREADS, 1)
 paf_kernel(const float* __restrict__ hms, int nchan, int h, int w, const float* __restrict__ peaks,
            float* __restrict__ scores, int dense_fill) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int hw = h * w;
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
-    float* planes = reinterpret_cast<float*>(smem_raw + 16);  // [2][hw]
-    float* pk = planes + 2 * hw;                              // [2][MAXP+1][2]  (x, y) of joint A then joint B
+    float* pk = reinterpret_cast<float*>(smem_raw + 16);  // [2][MAXP+1][2]  (x, y) of joint A then joint B
+    float* planes = pk + 4 * (MAXP + 1);                  // [2][hw] when STAGED (16-byte aligned: 16 + 2048 bytes in)
 
     const int l = blockIdx.x, img = blockIdx.y;
     const int partA = c_joint_pairs[2 * l], partB = c_joint_pairs[2 * l + 1];
@@ -206,7 +251,8 @@ paf_kernel(const float* __restrict__ hms, int nchan, int h, int w, const float* 
     const int nA = (int)pA[0], nB = (int)pB[0];
     if (nA > 0 && nB > 0) {
         const float* src = hms + ((size_t)img * nchan + NJ + 2 * l) * hw;
-        stage_planes(planes, src, (uint32_t)hw * 8u, bar);
+        if (STAGED) stage_planes(planes, src, (uint32_t)hw * 8u, bar);
+        const float* mapX = STAGED ? planes : src;
         for (int i = threadIdx.x; i < nA; i += PAF_THREADS) {
             pk[2 * i] = pA[3 * (i + 1)];
             pk[2 * i + 1] = pA[3 * (i + 1) + 1];
@@ -221,7 +267,7 @@ paf_kernel(const float* __restrict__ hms, int nchan, int h, int w, const float* 
         for (int p = threadIdx.x; p < npairs; p += PAF_THREADS) {
             const int a = p / nB, b = p - a * nB;
             out[a * MAXP + b] = paf_process(pk[2 * a], pk[2 * a + 1], pk[2 * (MAXP + 1) + 2 * b],
-                                            pk[2 * (MAXP + 1) + 2 * b + 1], planes, planes + hw, w, h, near_thr);
+                                            pk[2 * (MAXP + 1) + 2 * b + 1], mapX, mapX + hw, w, h, near_thr);
         }
     }
     if (dense_fill) {  // pafScoreKernel writes -1 outside nA x nB; only the extract() API needs it
@@ -747,26 +793,35 @@ lift_kernel(const float* __restrict__ bodies, const int* __restrict__ counts, co
 // ---------------------------------------------------------------------------------------------
 // host launchers
 // ---------------------------------------------------------------------------------------------
-static size_t nms_smem(int h, int w) {
-    const int hw = h * w;
-    return (size_t)hw * 4 + (size_t)((hw + 31) / 32) * 4 + (NMS_WARPS + 2) * 4 + 16;
+static int nms_bands(int h) {
+    const int b = (h + 31) / 32;
+    return b < 1 ? 1 : (b > NMS_MAX_BANDS ? NMS_MAX_BANDS : b);
 }
-static size_t paf_smem(int h, int w) { return (size_t)h * w * 8 + 4 * (MAXP + 1) * 4 + 16; }
+static int nms_rows(int h) { return (h + nms_bands(h) - 1) / nms_bands(h); }
+static size_t nms_smem(int h, int w) {
+    const int rows = nms_rows(h);
+    return 64 + (size_t)(rows + 6) * w * 4 + (size_t)((rows * w + 31) / 32) * 4;
+}
+static size_t paf_pk_bytes() { return 16 + 4 * (MAXP + 1) * 4; }
+static size_t paf_smem(int h, int w) { return paf_pk_bytes() + (size_t)h * w * 8; }
+static bool paf_staged(int h, int w) { return paf_smem(h, w) <= 232448; }
 
+// Any map size with w % 4 == 0 (16-byte bulk copies) whose NMS row band fits in shared memory; the reference hard-codes
+// 128 x 208 (extensions/association.cpp:21).
 int assoc_configure(int h, int w, const char** err) {
-    static const char* e_big = "association: heat-map plane too large for shared-memory staging (h*w*8 + 2 KB > 227 KB)";
-    static const char* e_align = "association: h*w must be a multiple of 4 (16-byte bulk copies)";
-    if ((h * w) % 4 != 0) {
+    static const char* e_big = "association: heat-map too large (an NMS row band of h/8 + 6 rows must fit in 227 KB of shared memory)";
+    static const char* e_align = "association: w must be a multiple of 4 (16-byte bulk copies)";
+    if (w % 4 != 0 || h < 3 || w < 4) {
         *err = e_align;
         return -1;
     }
-    if (paf_smem(h, w) > 232448 || nms_smem(h, w) > 232448) {
+    if (nms_smem(h, w) > 232448) {
         *err = e_big;
         return -1;
     }
     cudaError_t e = cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nms_smem(h, w));
-    if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(paf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)paf_smem(h, w));
+    if (e == cudaSuccess && paf_staged(h, w))
+        e = cudaFuncSetAttribute(paf_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)paf_smem(h, w));
     if (e != cudaSuccess) {
         *err = cudaGetErrorString(e);
         return -2;
@@ -775,12 +830,27 @@ int assoc_configure(int h, int w, const char** err) {
 }
 
 cudaError_t launch_nms(const float* hms, int nchan, int B, int h, int w, float thr, float* peaks, cudaStream_t st) {
-    nms_kernel<<<dim3(NJ, B), NMS_THREADS, nms_smem(h, w), st>>>(hms, nchan, h, w, thr, peaks);
-    return cudaGetLastError();
+    const int bands = nms_bands(h);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(bands, NJ, B);
+    cfg.blockDim = dim3(NMS_THREADS);
+    cfg.dynamicSmemBytes = nms_smem(h, w);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = bands;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, nms_kernel, hms, nchan, h, w, nms_rows(h), thr, peaks);
 }
 cudaError_t launch_paf(const float* hms, int nchan, int B, int h, int w, const float* peaks, float* scores,
                        int dense_fill, cudaStream_t st) {
-    paf_kernel<<<dim3(NL, B), PAF_THREADS, paf_smem(h, w), st>>>(hms, nchan, h, w, peaks, scores, dense_fill);
+    if (paf_staged(h, w))
+        paf_kernel<true><<<dim3(NL, B), PAF_THREADS, paf_smem(h, w), st>>>(hms, nchan, h, w, peaks, scores, dense_fill);
+    else
+        paf_kernel<false><<<dim3(NL, B), PAF_THREADS, paf_pk_bytes(), st>>>(hms, nchan, h, w, peaks, scores, dense_fill);
     return cudaGetLastError();
 }
 cudaError_t launch_group(const float* peaks, const float* scores, const float* rdepth, int B, int h, int w,

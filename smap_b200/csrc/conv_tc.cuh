@@ -53,6 +53,8 @@ struct alignas(64) ConvParams {
     long long plane_stride;  // elements between the hi and lo planes (= N*H*W*Cout)
     int relu;
     int one_group;  // debug: epilogue group 0 takes every chunk
+    int reverse;    // walk the tile list back to front (the consumer of a tensor starts with the rows its producer wrote
+                    // last, which are the ones still resident in L2)
     // fused bilinear residual (Upsample_unit, model/smap.py:211-217): tmR[0] is a low-resolution tensor [N,Hi,Wi,C];
     // the ring carries the (ph x pw)-pixel patch under each output tile and the epilogue interpolates
     // (align_corners=True) before the ReLU.  up_mode = 0: plain residual.
@@ -236,7 +238,8 @@ struct ConvCfg {
     static constexpr int SLOT_BYTES = TA * CHUNK_BYTES;  // hi (+ lo)
     static constexpr int OUT_BUFS = 2;  // one staging slot per epilogue group
     // RING: the layer streams epilogue inputs (residual / skip adds); without it the smem goes to operand stages
-    static constexpr int RES_BUFS = !RING ? 0 : (BLOCK_N >= 128) ? 4 : 2;
+    // (CTA pairs with BLOCK_N < 256 trade ring depth for a third operand stage)
+    static constexpr int RES_BUFS = !RING ? 0 : (CG == 2 && BLOCK_N < 256) ? 2 : (BLOCK_N >= 128) ? 4 : 2;
     static constexpr int SPG = RING ? RES_BUFS / 2 : 1;  // ring slots per epilogue group
     static constexpr int EPI_BYTES = (OUT_BUFS + RES_BUFS) * SLOT_BYTES;
     static constexpr int SMEM_LIMIT = 227 * 1024;
@@ -328,7 +331,8 @@ __global__ void __launch_bounds__(384, 1) conv_tc_kernel(const __grid_constant__
             uint32_t phase = 0;
             long long w_empty = 0;
             for (int tile = blockIdx.x / CG; tile < p.total_tiles; tile += gridDim.x / CG) {
-                const int nt = tile % p.n_tiles, mt = (tile / p.n_tiles) * CG + (int)cta_rank;
+                const int te = p.reverse ? p.total_tiles - 1 - tile : tile;
+                const int nt = te % p.n_tiles, mt = (te / p.n_tiles) * CG + (int)cta_rank;
                 const int img = mt / tiles_per_img, r = mt - img * tiles_per_img;
                 const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
                 const int x_in0 = (tx << p.tw_log2) * p.stride - p.pad_x;
@@ -440,7 +444,8 @@ __global__ void __launch_bounds__(384, 1) conv_tc_kernel(const __grid_constant__
             int cnt[2] = {0, 0};  // fills issued so far per group
             const int one = p.one_group;
             for (int tile = blockIdx.x / CG; tile < p.total_tiles; tile += gridDim.x / CG) {
-                const int nt = tile % p.n_tiles, mt = (tile / p.n_tiles) * CG + (int)cta_rank;
+                const int te = p.reverse ? p.total_tiles - 1 - tile : tile;
+                const int nt = te % p.n_tiles, mt = (te / p.n_tiles) * CG + (int)cta_rank;
                 const int img = mt / tiles_per_img, r = mt - img * tiles_per_img;
                 const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
                 for (int c = 0; c < Cfg::CHUNKS; c++) {
@@ -477,7 +482,8 @@ __global__ void __launch_bounds__(384, 1) conv_tc_kernel(const __grid_constant__
         int rcnt = 0;
         long long w_tfull = 0, w_stage = 0;
         for (int tile = blockIdx.x / CG; tile < p.total_tiles; tile += gridDim.x / CG) {
-            const int nt = tile % p.n_tiles, mt = (tile / p.n_tiles) * CG + (int)cta_rank;
+            const int te = p.reverse ? p.total_tiles - 1 - tile : tile;
+            const int nt = te % p.n_tiles, mt = (te / p.n_tiles) * CG + (int)cta_rank;
             const int img = mt / tiles_per_img, r = mt - img * tiles_per_img;
             const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
             const int py = ty * p.th + (row >> p.tw_log2);

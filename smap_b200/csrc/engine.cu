@@ -1,7 +1,9 @@
 // Host side of libsmap_b200: handle, weight folding/repack, execution plan, C ABI (include/smap_b200.h).
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 #include <math.h>
+#include <nvtx3/nvToolsExt.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -9,6 +11,7 @@
 #include <algorithm>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -28,6 +31,13 @@ namespace {
 // small utilities
 // ------------------------------------------------------------------------------------------------
 thread_local std::string g_create_error = "";
+
+// Process-wide tile-shape table: layer geometry -> (BLOCK_N, CTA-group size).  Filled from the committed table
+// (smapb_set_tile_table) and, for geometries it does not cover, by the autotuner.  Being process-wide, every handle of a
+// process runs a given layer with the same tile shape; across processes the committed table (or a broadcast of rank 0's
+// table, smap_b200.dist.sync_tile_table) gives the same guarantee.
+std::mutex g_tiles_mu;
+std::map<std::string, std::pair<int, int>> g_tiles;
 
 inline uint16_t f32_to_bf16_rn(float f) {
     uint32_t u;
@@ -98,6 +108,7 @@ struct Op {
     std::vector<int> waits;  // indices of producer ops on the OTHER stream this op must wait for
     bool record = false;     // some op on the other stream consumes this op's output
     cudaEvent_t ev = nullptr;
+    std::string name;  // reference unit name (NVTX range, profiles)
 };
 
 struct Plan {
@@ -152,22 +163,36 @@ struct smapb_handle {
         float* imgs = nullptr;
         double* scales = nullptr;
         smapb_record* records = nullptr;
+        smapb_record* records_all = nullptr;  // [comm_world * max_batch], gathered variant
         cudaEvent_t h2d = nullptr, done = nullptr;
         bool used = false;
     } slots[2];
     cudaStream_t copy_stream = nullptr;
-    std::map<std::string, std::pair<int, int>> tune_cache;  // layer geometry -> measured best (BLOCK_N, CG)
     bool autotune = getenv("SMAPB_NO_AUTOTUNE") == nullptr;
     bool two_streams = getenv("SMAPB_ONE_STREAM") == nullptr;  // side branches (heads, skip convs) on a second stream
     cudaStream_t aux_stream = nullptr;  // side branches of the decoder (skip convs, heads) run here
-    cudaStream_t own_stream = nullptr;  // blocking stream used when the caller passes the legacy default stream
+    // Stream used when the caller passes NULL (= the legacy default stream).  It is NON-blocking - a blocking stream would
+    // be fenced by every legacy-stream operation of the process (e.g. a collective issued by the host framework) - and is
+    // ordered against the legacy stream explicitly with the two bridge events (legacy_enter / legacy_leave).
+    cudaStream_t own_stream = nullptr;
+    cudaEvent_t bridge_in = nullptr, bridge_out = nullptr;
     struct GraphEntry {
-        int B, flip;
+        int B, flip, gather;
         const void* imgs;
         const void* scales;
         cudaGraphExec_t exec;
+        uint64_t stamp;  // last use (LRU eviction)
     };
-    std::vector<GraphEntry> graphs;  // whole-path CUDA graphs keyed by (B, flip, input pointers)
+    std::vector<GraphEntry> graphs;  // whole-path CUDA graphs keyed by (B, flip, gather, input pointers)
+    uint64_t graph_clock = 0;
+    // skeleton-record exchange: one ncclAllGather per batch on the compute stream, inside the graph
+    void* comm = nullptr;  // ncclComm_t
+    bool comm_owned = false;
+    int comm_rank = 0, comm_world = 1;
+    smapb_record* gather_dev = nullptr;  // [comm_world * max_batch]
+    bool nccl_in_graph = getenv("SMAPB_NCCL_EAGER") == nullptr;
+    bool nvtx_ops = getenv("SMAPB_NVTX") != nullptr;  // one NVTX range per plan op (phase ranges are always emitted)
+    bool serpentine = getenv("SMAPB_SERPENTINE") != nullptr;
     // pre-processing: resampling tables per source geometry, staging for host images
     struct PreEntry {
         ResizePlan plan;
@@ -204,6 +229,71 @@ int fail(smapb_handle* h, int code, const std::string& msg) {
         if (e_ != cudaSuccess)                                                                            \
             return fail(h, -10, std::string(#call) + ": " + cudaGetErrorString(e_) + " @" + std::to_string(__LINE__)); \
     } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// NCCL, bound at run time (dlopen): libsmap_b200.so has no link-time dependency on it, and inside a PyTorch process
+// dlopen("libnccl.so.2") resolves to the instance torch already loaded, so a communicator created by the host framework
+// (ProcessGroupNCCL._comm_ptr) and one created here (smapb_comm_create) are served by the same library.
+// ------------------------------------------------------------------------------------------------
+struct NcclUid {  // ncclUniqueId
+    char internal[128];
+};
+struct NcclApi {
+    void* lib = nullptr;
+    int (*GetUniqueId)(NcclUid*) = nullptr;
+    int (*CommInitRank)(void**, int, NcclUid, int) = nullptr;  // (ncclComm_t*, nranks, id by value, rank)
+    int (*CommDestroy)(void*) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    int (*GetVersion)(int*) = nullptr;
+    std::string err;
+};
+NcclApi& nccl_api() {
+    static NcclApi api;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        const char* names[] = {getenv("SMAPB_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+        for (const char* n : names) {
+            if (!n) continue;
+            api.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+            if (api.lib) break;
+        }
+        if (!api.lib) {
+            api.err = std::string("NCCL not found (dlopen libnccl.so.2): ") + (dlerror() ? dlerror() : "");
+            return;
+        }
+        api.GetUniqueId = (int (*)(NcclUid*))dlsym(api.lib, "ncclGetUniqueId");
+        api.CommInitRank = (int (*)(void**, int, NcclUid, int))dlsym(api.lib, "ncclCommInitRank");
+        api.CommDestroy = (int (*)(void*))dlsym(api.lib, "ncclCommDestroy");
+        api.AllGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))dlsym(api.lib, "ncclAllGather");
+        api.GetErrorString = (const char* (*)(int))dlsym(api.lib, "ncclGetErrorString");
+        api.GetVersion = (int (*)(int*))dlsym(api.lib, "ncclGetVersion");
+        if (!api.GetUniqueId || !api.CommInitRank || !api.CommDestroy || !api.AllGather) {
+            api.err = "NCCL library lacks a required symbol";
+            api.lib = nullptr;
+        }
+    });
+    return api;
+}
+int nccl_fail(smapb_handle* h, const char* what, int rc) {
+    NcclApi& a = nccl_api();
+    return fail(h, -50, std::string(what) + ": " + (a.GetErrorString ? a.GetErrorString(rc) : "NCCL error") + " (" +
+                            std::to_string(rc) + ")");
+}
+
+// NULL-stream callers (the legacy default stream): order the handle's non-blocking stream after the legacy stream's
+// pending work, and - on the way out - the legacy stream after ours, which is what a blocking stream would give them,
+// without fencing every other stream of the process.
+int legacy_enter(smapb_handle* h) {
+    CK(cudaEventRecord(h->bridge_in, cudaStreamLegacy));
+    CK(cudaStreamWaitEvent(h->own_stream, h->bridge_in, 0));
+    return 0;
+}
+int legacy_leave(smapb_handle* h) {
+    CK(cudaEventRecord(h->bridge_out, h->own_stream));
+    CK(cudaStreamWaitEvent(cudaStreamLegacy, h->bridge_out, 0));
+    return 0;
+}
 
 enum ProfKind { PK_START = -1, PK_CONV = 0, PK_STEM = 1, PK_ELEM = 2, PK_ASSOC = 3, PK_LIFT = 4, PK_COPY = 5 };
 void prof_mark(smapb_handle* h, int kind, cudaStream_t st, const char* desc = "", double flops = 0) {
@@ -313,8 +403,13 @@ cudaError_t launch_conv_inst(const ConvParams& cp, int sm_count, cudaStream_t st
 }
 cudaError_t launch_conv(const ConvParams& cp, int block_n, int nterms, int sm_count, cudaStream_t st, bool pdl,
                         int cg = 1) {
-    if (cg == 2) {  // CTA pairs: 256 x 256 tiles, bf16x3 only
-        if (block_n == 256 && nterms == 3) return launch_conv_inst<256, 3, 2>(cp, sm_count, st, pdl);
+    if (cg == 2) {  // CTA pairs (cta_group::2): 256 x {256,128,64} tiles, bf16x3 only
+        if (nterms != 3) return cudaErrorInvalidValue;
+        switch (block_n) {
+            case 256: return launch_conv_inst<256, 3, 2>(cp, sm_count, st, pdl);
+            case 128: return launch_conv_inst<128, 3, 2>(cp, sm_count, st, pdl);
+            case 64: return launch_conv_inst<64, 3, 2>(cp, sm_count, st, pdl);
+        }
         return cudaErrorInvalidValue;
     }
 #define SMAPB_CASE(BN)                                                                  \
@@ -433,7 +528,8 @@ int setup_conv(smapb_handle* h, const ConvLayer& L, const Act& in, const Act* re
     }
     if (!force_bn && getenv("SMAPB_FORCE_TILE")) {  // debug: "bn,cg" for every layer where it is valid
         int fb = 0, fc = 1;
-        if (sscanf(getenv("SMAPB_FORCE_TILE"), "%d,%d", &fb, &fc) >= 1 && L.Cout_pad % fb == 0 && !(fc == 2 && (outf || !cg_out)))
+        if (sscanf(getenv("SMAPB_FORCE_TILE"), "%d,%d", &fb, &fc) >= 1 && fb > 0 && L.Cout_pad % fb == 0 &&
+            !(fc == 2 && (outf || !cg_out || fb < 64)) && !(fc != 2 && fb == 256 && (res || post1 || up)))
             force_bn = fb, force_cg = fc;
     }
     if (force_bn) {  // autotuner override
@@ -441,7 +537,7 @@ int setup_conv(smapb_handle* h, const ConvLayer& L, const Act& in, const Act* re
         cg = force_cg ? force_cg : 1;
         // one-CTA 128 x 256 tiles in bf16x3 have room for two 96 KB operand stages only without an epilogue-input ring
         const bool needs_ring = res || post1 || up;
-        if (L.Cout_pad % bn || (cg == 2 && (bn != 256 || h->nterms != 3 || outf || !cg_out)) ||
+        if (L.Cout_pad % bn || (cg == 2 && ((bn != 256 && bn != 128 && bn != 64) || h->nterms != 3 || outf || !cg_out)) ||
             (cg == 1 && bn == 256 && h->nterms == 3 && needs_ring))
             return fail(h, -31, "invalid forced tile");
     }
@@ -615,6 +711,15 @@ int upload_conv_layer(smapb_handle* h, ConvLayer& L, const std::vector<float>& w
 
 int pad32(int c) { return (c + 31) / 32 * 32; }
 
+void free_plan(Plan* plan) {
+    if (plan->graph) cudaGraphExecDestroy(plan->graph);
+    for (void* p : plan->allocs) cudaFree(p);
+    for (Op& op : plan->ops)
+        if (op.ev) cudaEventDestroy(op.ev);
+    plan->allocs.clear();
+    plan->ops.clear();
+}
+
 // ------------------------------------------------------------------------------------------------
 // plan
 // ------------------------------------------------------------------------------------------------
@@ -668,6 +773,15 @@ struct PlanBuilder {
         a.ptr = (float*)p;
         return a;
     }
+    // SMAPB_SERPENTINE: a conv walks its tile list in the opposite direction of the op that produced its input, so that it
+    // starts with the rows written last (still in L2) instead of the ones written first (evicted by then)
+    int reverse_for(const void* in_ptr) {
+        if (!h->serpentine) return 0;
+        auto it = plan->producer.find(in_ptr);
+        if (it == plan->producer.end()) return 1;
+        const Op& prod = plan->ops[it->second];
+        return prod.kind == OP_CONV ? !prod.cp.reverse : 1;
+    }
     const ConvLayer* layer(const std::string& name) {
         auto it = h->layers.find(name);
         if (it == h->layers.end()) {
@@ -684,16 +798,20 @@ struct PlanBuilder {
         snprintf(key, sizeof key, "%d/%d/%d k%d s%d %dx%dx%d r%d p%d u%d c2_%d s2_%d t%d", L.Cin, L.Cout_pad, L.Cin2, L.k,
                  L.stride, in.N, in.H, in.W, res ? 1 : 0, (p1 ? 1 : 0) + (p2 ? 1 : 0), up ? 1 : 0, L.Cin2, L.stride2,
                  h->nterms);
-        auto it = h->tune_cache.find(key);
         int best_bn = 0, best_cg = 1;
-        if (it != h->tune_cache.end()) {
-            best_bn = it->second.first, best_cg = it->second.second;
-        } else {
+        bool known = false;
+        {
+            std::lock_guard<std::mutex> lk(g_tiles_mu);
+            auto it = g_tiles.find(key);
+            if (it != g_tiles.end()) best_bn = it->second.first, best_cg = it->second.second, known = true;
+        }
+        if (!known && !h->autotune) return 0;  // cost model (deterministic)
+        if (!known) {
             cudaEvent_t e0, e1;
             cudaEventCreate(&e0);
             cudaEventCreate(&e1);
             float best_ms = 1e30f;
-            const int cand[5][2] = {{128, 1}, {64, 1}, {256, 2}, {256, 1}, {32, 1}};
+            const int cand[7][2] = {{128, 1}, {64, 1}, {256, 2}, {128, 2}, {64, 2}, {256, 1}, {32, 1}};
             for (auto& c : cand) {
                 if (L.Cout_pad % c[0]) continue;
                 if (c[1] == 2 && h->nterms != 3) continue;
@@ -722,7 +840,9 @@ struct PlanBuilder {
             cudaEventDestroy(e1);
             h->err.clear();
             if (!best_bn) return 0;  // keep the model's choice
-            h->tune_cache[key] = {best_bn, best_cg};
+            std::lock_guard<std::mutex> lk(g_tiles_mu);
+            auto ins = g_tiles.emplace(key, std::make_pair(best_bn, best_cg));
+            best_bn = ins.first->second.first, best_cg = ins.first->second.second;  // another handle may have been first
         }
         if (best_bn == op->block_n && best_cg == op->cg) return 0;
         return setup_conv(h, L, in, res, p1, p2, out, nullptr, relu, &op->cp, &op->block_n, &op->flops, in2, up, &op->cg,
@@ -740,7 +860,9 @@ struct PlanBuilder {
         Op op;
         op.kind = OP_CONV;
         rc = setup_conv(h, *L, in, res, p1, p2, &out, nullptr, relu, &op.cp, &op.block_n, &op.flops, in2, up, &op.cg);
-        if (!rc && h->autotune) rc = tune(*L, in, res, p1, p2, &out, relu, in2, up, &op);
+        if (!rc) rc = tune(*L, in, res, p1, p2, &out, relu, in2, up, &op);
+        op.name = name;
+        op.cp.reverse = reverse_for(in.ptr);
         plan->ops.push_back(op);
         wire(out.ptr, {in.ptr, res ? res->ptr : nullptr, p1 ? p1->ptr : nullptr, p2 ? p2->ptr : nullptr,
                        in2 ? in2->ptr : nullptr, up ? up->ptr : nullptr});
@@ -758,6 +880,8 @@ struct PlanBuilder {
         Op op;
         op.kind = OP_CONV;
         rc = setup_conv(h, *L, in, nullptr, nullptr, nullptr, nullptr, &out, 0, &op.cp, &op.block_n, &op.flops);
+        op.name = name;
+        op.cp.reverse = reverse_for(in.ptr);
         plan->ops.push_back(op);
         wire(out.ptr, {in.ptr});
         plan->n_conv++;
@@ -804,6 +928,8 @@ int build_plan(smapb_handle* h, int B, Plan** out_plan, int instance = 0) {
                 h->stem_tc_ok = 1;
                 Op os;
                 os.kind = OP_S2D;
+                os.name = "top.s2d";
+                oc.name = "top.conv";
                 os.out = s2d;
                 plan->ops.push_back(os);
                 pb.wire(s2d.ptr, {});
@@ -825,6 +951,7 @@ int build_plan(smapb_handle* h, int B, Plan** out_plan, int instance = 0) {
     {
         Op op;
         op.kind = OP_MAXPOOL;
+        op.name = "top.maxpool";
         op.a = stem;
         op.out = x;
         plan->ops.push_back(op);
@@ -918,12 +1045,13 @@ int build_plan(smapb_handle* h, int B, Plan** out_plan, int instance = 0) {
         x = cross;
     }
     if (pb.rc) {
-        for (void* p : plan->allocs) cudaFree(p);
+        free_plan(plan.get());
         return pb.rc;
     }
     {
         Op op;
         op.kind = OP_HEADMERGE;
+        op.name = "head_merge(res4+res3+res2)";
         op.f4 = res[3], op.f3 = res[2], op.f2 = res[1];
         op.cout = 43;
         op.which_out = 0;
@@ -931,6 +1059,7 @@ int build_plan(smapb_handle* h, int B, Plan** out_plan, int instance = 0) {
         pb.wire(nullptr, {res[3].ptr, res[2].ptr, res[1].ptr});
         Op od;
         od.kind = OP_TAPSUM;
+        od.name = "tapsum(res_d)";
         od.f4 = resd3;
         od.cout = 14;
         od.which_out = 1;
@@ -939,6 +1068,7 @@ int build_plan(smapb_handle* h, int B, Plan** out_plan, int instance = 0) {
         pb.wire(nullptr, {resd3.ptr});
         Op ord_;
         ord_.kind = OP_TAPSUM;
+        ord_.name = "tapsum(res_rd)";
         ord_.f4 = resrd3;
         ord_.cout = 1;
         ord_.which_out = 2;
@@ -974,6 +1104,7 @@ int run_plan(smapb_handle* h, Plan* plan, const float* imgs, float* hm2d, float*
         st = (multi && op.stream == 1) ? h->aux_stream : main_st;
         if (multi)
             for (int w : op.waits) CK(cudaStreamWaitEvent(st, plan->ops[w].ev, 0));
+        if (h->nvtx_ops) nvtxRangePushA(op.name.empty() ? "smapb.op" : op.name.c_str());
         switch (op.kind) {
             case OP_STEM:
                 CK(launch_stem(imgs, h->stem_w, h->stem_b, B, h->in_h, h->in_w, op.out.ptr, op.out.plane(), T, st));
@@ -1016,6 +1147,7 @@ int run_plan(smapb_handle* h, Plan* plan, const float* imgs, float* hm2d, float*
                 break;
             }
         }
+        if (h->nvtx_ops) nvtxRangePop();
         h->launches++;
         if (multi && op.record) CK(cudaEventRecord(op.ev, st));
         static const bool debug_sync = getenv("SMAPB_DEBUG_SYNC") != nullptr;
@@ -1032,7 +1164,7 @@ int run_plan(smapb_handle* h, Plan* plan, const float* imgs, float* hm2d, float*
 extern "C" {
 #pragma GCC visibility push(default)
 
-int smapb_version(void) { return 100; }
+int smapb_version(void) { return 200; }
 
 const char* smapb_last_error(const smapb_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 
@@ -1081,8 +1213,14 @@ int smapb_create(smapb_handle** out, int device, int max_batch, int in_h, int in
         delete h;
         return -10;
     }
-    if (cudaStreamCreate(&h->own_stream) != cudaSuccess) h->own_stream = nullptr;
-    cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking);
+    if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->bridge_in, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->bridge_out, cudaEventDisableTiming) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        g_create_error = "smapb_create: stream / event creation failed";
+        smapb_destroy(h);
+        return -10;
+    }
     const char* aerr = nullptr;
     // association kernels stage whole planes in shared memory; larger maps are rejected at call time
     if (assoc_configure(h->h, h->w, &aerr) != 0) h->err = aerr ? aerr : "assoc_configure failed";
@@ -1093,22 +1231,24 @@ int smapb_create(smapb_handle** out, int device, int max_batch, int in_h, int in
 void smapb_destroy(smapb_handle* h) {
     if (!h) return;
     cudaSetDevice(h->device);
-    for (auto& kv : h->plans) {
-        if (kv.second->graph) cudaGraphExecDestroy(kv.second->graph);
-        for (void* p : kv.second->allocs) cudaFree(p);
-        for (Op& op : kv.second->ops)
-            if (op.ev) cudaEventDestroy(op.ev);
-    }
+    cudaDeviceSynchronize();
+    for (auto& kv : h->plans) free_plan(kv.second.get());
     for (auto& g : h->graphs) cudaGraphExecDestroy(g.exec);
     for (auto& S : h->slots) {
         cudaFree(S.imgs);
         cudaFree(S.scales);
         cudaFree(S.records);
+        cudaFree(S.records_all);
         if (S.h2d) cudaEventDestroy(S.h2d);
         if (S.done) cudaEventDestroy(S.done);
     }
+    if (h->comm && h->comm_owned && nccl_api().CommDestroy) nccl_api().CommDestroy(h->comm);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    if (h->aux_stream) cudaStreamDestroy(h->aux_stream);
+    if (h->bridge_in) cudaEventDestroy(h->bridge_in);
+    if (h->bridge_out) cudaEventDestroy(h->bridge_out);
+    for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
     for (auto& kv : h->layers) {
         cudaFree(kv.second.w_dev);
         cudaFree(kv.second.bias_dev);
@@ -1116,7 +1256,8 @@ void smapb_destroy(smapb_handle* h) {
     cudaFree(h->stem_tc.w_dev);
     cudaFree(h->stem_tc.bias_dev);
     void* ptrs[] = {h->peaks, h->scores, h->bodies, h->counts, h->imgs_dev, h->imgs_flip, h->hm, h->hm_flip, h->detd,
-                    h->rootd, h->scratch_detd, h->scratch_rootd, h->scales_dev, h->records_dev, h->stem_w, h->stem_b};
+                    h->rootd, h->scratch_detd, h->scratch_rootd, h->scales_dev, h->records_dev, h->stem_w, h->stem_b,
+                    h->gather_dev};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (h->refine_buf) cudaFree(h->refine_buf);
@@ -1152,10 +1293,8 @@ int smapb_finalize_weights(smapb_handle* h, int precision) {
     h->graphs.clear();
     h->eager_runs.clear();
     if (new_planes != h->planes || !h->plans.empty()) {
-        for (auto& kv : h->plans) {
-            if (kv.second->graph) cudaGraphExecDestroy(kv.second->graph);
-            for (void* p : kv.second->allocs) cudaFree(p);
-        }
+        cudaDeviceSynchronize();
+        for (auto& kv : h->plans) free_plan(kv.second.get());
         h->plans.clear();
         for (auto& kv : h->layers) {
             cudaFree(kv.second.w_dev);
@@ -1323,9 +1462,12 @@ int smapb_backbone_forward(smapb_handle* h, const float* imgs, int B, float* hm2
     Plan* plan = nullptr;
     int rc = build_plan(h, B, &plan);
     if (rc) return rc;
-    // NULL = legacy default stream: run on the handle's own blocking stream (ordered with the caller's default-stream
-    // work by legacy-stream semantics, but concurrent with other handles)
-    return run_plan(h, plan, imgs, hm2d, detd, rootd, stream ? (cudaStream_t)stream : h->own_stream);
+    // NULL = legacy default stream: run on the handle's own (non-blocking) stream, bridged to the legacy stream on both sides
+    if (stream) return run_plan(h, plan, imgs, hm2d, detd, rootd, (cudaStream_t)stream);
+    rc = legacy_enter(h);
+    if (!rc) rc = run_plan(h, plan, imgs, hm2d, detd, rootd, h->own_stream);
+    if (!rc) rc = legacy_leave(h);
+    return rc;
 }
 
 int smapb_merge_scale(smapb_handle* h, float* hm2d, const float* hm2d_flip, int B, int do_scale, void* stream) {
@@ -1404,10 +1546,14 @@ static int pre_entry(smapb_handle* h, int img_h, int img_w, smapb_handle::PreEnt
         int* yo = xo + nx;
         short* xc = (short*)(yo + ny);
         short* yc = xc + 2 * nx;
-        CK(cudaMemcpy(xo, P.xofs.data(), nx * 4, cudaMemcpyHostToDevice));
-        CK(cudaMemcpy(yo, P.yofs.data(), ny * 4, cudaMemcpyHostToDevice));
-        CK(cudaMemcpy(xc, P.xcoef.data(), nx * 2 * 2, cudaMemcpyHostToDevice));
-        CK(cudaMemcpy(yc, P.ycoef.data(), ny * 2, cudaMemcpyHostToDevice));
+        cudaError_t ce = cudaMemcpy(xo, P.xofs.data(), nx * 4, cudaMemcpyHostToDevice);
+        if (ce == cudaSuccess) ce = cudaMemcpy(yo, P.yofs.data(), ny * 4, cudaMemcpyHostToDevice);
+        if (ce == cudaSuccess) ce = cudaMemcpy(xc, P.xcoef.data(), nx * 2 * 2, cudaMemcpyHostToDevice);
+        if (ce == cudaSuccess) ce = cudaMemcpy(yc, P.ycoef.data(), ny * 2, cudaMemcpyHostToDevice);
+        if (ce != cudaSuccess) {
+            cudaFree(E.buf);
+            return fail(h, -10, std::string("smapb_preprocess: table upload: ") + cudaGetErrorString(ce));
+        }
         E.tab = {xo, xc, yo, yc};
         it = h->pre_cache.emplace(key, std::move(E)).first;
     }
@@ -1581,8 +1727,12 @@ __global__ void flip_w_kernel(const float* __restrict__ in, float* __restrict__ 
 
 static int infer_body(smapb_handle* h, Plan* plan, const float* imgs, const double* scales, int B, int do_flip,
                       smapb_record* records, cudaStream_t st) {
+    nvtxRangePushA("smapb.backbone");
     int rc = run_plan(h, plan, imgs, h->hm, h->detd, h->rootd, st);
-    if (rc) return rc;
+    if (rc) {
+        nvtxRangePop();
+        return rc;
+    }
     const size_t hw = (size_t)h->h * h->w;
     if (do_flip) {
         const size_t MB = h->max_batch;
@@ -1597,8 +1747,13 @@ static int infer_body(smapb_handle* h, Plan* plan, const float* imgs, const doub
         prof_mark(h, PK_ELEM, st, "flip_w");
         h->launches++;
         rc = run_plan(h, plan, h->imgs_flip, h->hm_flip, h->scratch_detd, h->scratch_rootd, st);
-        if (rc) return rc;
+        if (rc) {
+            nvtxRangePop();
+            return rc;
+        }
     }
+    nvtxRangePop();
+    nvtxRangePushA("smapb.association");
     CK(launch_merge_scale(h->hm, do_flip ? h->hm_flip : nullptr, B, h->h, h->w, 1, st));
     prof_mark(h, PK_ELEM, st, "merge_scale");
     CK(launch_nms(h->hm, NC2D, B, h->h, h->w, 0.2f, h->peaks, st));
@@ -1607,6 +1762,8 @@ static int infer_body(smapb_handle* h, Plan* plan, const float* imgs, const doub
     prof_mark(h, PK_ASSOC, st, "paf");
     CK(launch_group(h->peaks, h->scores, h->rootd, B, h->h, h->w, 2, 1, h->bodies, h->counts, st));
     prof_mark(h, PK_ASSOC, st, "group");
+    nvtxRangePop();
+    nvtxRangePushA("smapb.lift");
     char* rb = reinterpret_cast<char*>(records);
     CK(launch_lift(h->bodies, h->counts, h->detd, h->rootd, scales, B, h->h, h->w, 2,
                    reinterpret_cast<float*>(rb + offsetof(smapb_record, pred2d)),
@@ -1624,40 +1781,63 @@ static int infer_body(smapb_handle* h, Plan* plan, const float* imgs, const doub
         prof_mark(h, PK_LIFT, st, "refine");
         h->launches++;
     }
+    nvtxRangePop();
     return 0;
 }
 
-int smapb_infer_device(smapb_handle* h, const float* imgs, const double* scales, int B, int do_flip,
-                       smapb_record* records, void* stream) {
-    if (!h) return -1;
-    if (!h->finalized) return fail(h, -2, "smapb_infer_device: weights not finalized");
-    cudaSetDevice(h->device);
+// one all-gather of B fixed-stride records per rank, on `st`
+static int gather_records(smapb_handle* h, void* comm, const smapb_record* send, smapb_record* recv, int B, cudaStream_t st) {
+    NcclApi& a = nccl_api();
+    if (!a.lib) return fail(h, -51, a.err.empty() ? "NCCL unavailable" : a.err);
+    if (!comm) return fail(h, -52, "no NCCL communicator");
+    const int rc = a.AllGather(send, recv, (size_t)B * sizeof(smapb_record), /* ncclUint8 */ 1, comm, st);
+    if (rc != 0) return nccl_fail(h, "ncclAllGather", rc);
+    return 0;
+}
+
+// Whole path on stream `st` (never NULL here).  gather != 0: followed by the all-gather of the records over the handle's
+// communicator; `records` then receives comm_world * B records in rank order.
+static int infer_device_impl(smapb_handle* h, const float* imgs, const double* scales, int B, int do_flip, int gather,
+                             smapb_record* records, cudaStream_t st) {
     int rc = check_assoc(h, B);
     if (rc) return rc;
-    // The legacy default stream cannot be captured: run on the handle's own blocking stream instead (legacy-stream
-    // semantics keep it ordered with the caller's default-stream work on both sides).
-    cudaStream_t st = stream ? (cudaStream_t)stream : h->own_stream;
+    if (gather && !h->comm) return fail(h, -52, "smapb_infer_*_gather: no communicator attached (smapb_comm_create / smapb_comm_attach)");
+    if (gather && !h->gather_dev) return fail(h, -52, "gather buffer missing");
     Plan* plan = nullptr;
     rc = build_plan(h, B, &plan);
     if (rc) return rc;
     do_flip = do_flip ? 1 : 0;
+    gather = gather ? 1 : 0;
+    const size_t out_records = (size_t)B * (gather ? h->comm_world : 1);
     static const bool no_graph = getenv("SMAPB_NO_GRAPH") != nullptr;
-    // The whole path (~230 launches) is replayed from a CUDA graph: the first two calls for a (B, flip) run eagerly
-    // (lazy allocations, function attributes), then one graph per distinct input pointer pair is captured.  Results
-    // land in the handle's record buffer and are copied to the caller's pointer after the graph.
-    int& eager = h->eager_runs[{B, do_flip}];
-    if (no_graph || h->profiling || eager < 2 || st == nullptr) {
+    // The whole path (~210 launches) is replayed from a CUDA graph: the first two calls for a (B, flip, gather) run
+    // eagerly (lazy allocations, function attributes, NCCL connection setup), then one graph per distinct input pointer
+    // pair is captured - with the all-gather inside when NCCL accepts the capture.  Results land in handle-owned
+    // buffers and are copied to the caller's pointer behind the graph.
+    int& eager = h->eager_runs[{B, do_flip * 2 + gather}];
+    if (no_graph || h->profiling || eager < 2) {
         eager++;
-        return infer_body(h, plan, imgs, scales, B, do_flip, records, st);
+        if (!gather) return infer_body(h, plan, imgs, scales, B, do_flip, records, st);
+        rc = infer_body(h, plan, imgs, scales, B, do_flip, h->records_dev, st);
+        if (rc) return rc;
+        return gather_records(h, h->comm, h->records_dev, records, B, st);
     }
     smapb_handle::GraphEntry* ge = nullptr;
     for (auto& g : h->graphs)
-        if (g.B == B && g.flip == do_flip && g.imgs == imgs && g.scales == scales) ge = &g;
+        if (g.B == B && g.flip == do_flip && g.gather == gather && g.imgs == imgs && g.scales == scales) ge = &g;
+    const bool gather_in_graph = gather && h->nccl_in_graph;
     if (!ge) {
-        if (h->graphs.size() >= 32) return infer_body(h, plan, imgs, scales, B, do_flip, records, st);
+        if (h->graphs.size() >= 16) {  // evict the least recently used graph (callers that pass ever-changing pointers)
+            size_t lru = 0;
+            for (size_t i = 1; i < h->graphs.size(); i++)
+                if (h->graphs[i].stamp < h->graphs[lru].stamp) lru = i;
+            cudaGraphExecDestroy(h->graphs[lru].exec);
+            h->graphs.erase(h->graphs.begin() + lru);
+        }
         const int64_t launches_before = h->launches;
         CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
         rc = infer_body(h, plan, imgs, scales, B, do_flip, h->records_dev, st);
+        if (!rc && gather_in_graph) rc = gather_records(h, h->comm, h->records_dev, h->gather_dev, B, st);
         cudaGraph_t graph = nullptr;
         cudaError_t ce = cudaStreamEndCapture(st, &graph);
         h->launches = launches_before;
@@ -1670,37 +1850,75 @@ int smapb_infer_device(smapb_handle* h, const float* imgs, const double* scales,
         ce = cudaGraphInstantiate(&exec, graph, 0);
         cudaGraphDestroy(graph);
         if (ce != cudaSuccess) return fail(h, -10, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ce));
-        h->graphs.push_back({B, do_flip, imgs, scales, exec});
+        h->graphs.push_back({B, do_flip, gather, imgs, scales, exec, 0});
         ge = &h->graphs.back();
     }
+    ge->stamp = ++h->graph_clock;
     CK(cudaGraphLaunch(ge->exec, st));
     h->launches += (int64_t)plan->ops.size() * (do_flip ? 2 : 1) + 5 + (do_flip ? 1 : 0) + (h->refine_on ? 1 : 0);
-    if (records != h->records_dev)
-        CK(cudaMemcpyAsync(records, h->records_dev, (size_t)B * sizeof(smapb_record), cudaMemcpyDeviceToDevice, st));
+    const smapb_record* src = h->records_dev;
+    if (gather) {
+        if (!gather_in_graph) {  // NCCL outside the graph, still stream-ordered on the compute stream
+            rc = gather_records(h, h->comm, h->records_dev, h->gather_dev, B, st);
+            if (rc) return rc;
+        }
+        src = h->gather_dev;
+    }
+    if (records != src)
+        CK(cudaMemcpyAsync(records, src, out_records * sizeof(smapb_record), cudaMemcpyDeviceToDevice, st));
     return 0;
+}
+
+static int infer_device_entry(smapb_handle* h, const float* imgs, const double* scales, int B, int do_flip, int gather,
+                              smapb_record* records, void* stream) {
+    if (!h) return -1;
+    if (!h->finalized) return fail(h, -2, "smapb_infer_device: weights not finalized");
+    cudaSetDevice(h->device);
+    if (stream) return infer_device_impl(h, imgs, scales, B, do_flip, gather, records, (cudaStream_t)stream);
+    // The legacy default stream cannot be captured: run on the handle's own stream, bridged on both sides
+    int rc = legacy_enter(h);
+    if (!rc) rc = infer_device_impl(h, imgs, scales, B, do_flip, gather, records, h->own_stream);
+    if (!rc) rc = legacy_leave(h);
+    return rc;
+}
+
+int smapb_infer_device(smapb_handle* h, const float* imgs, const double* scales, int B, int do_flip,
+                       smapb_record* records, void* stream) {
+    return infer_device_entry(h, imgs, scales, B, do_flip, 0, records, stream);
+}
+
+int smapb_infer_device_gather(smapb_handle* h, const float* imgs, const double* scales, int B, int do_flip,
+                              smapb_record* all_records, void* stream) {
+    return infer_device_entry(h, imgs, scales, B, do_flip, 1, all_records, stream);
 }
 
 int smapb_infer_host(smapb_handle* h, const float* imgs_host, const double* scales_host, int B, int do_flip,
                      smapb_record* records_host, void* stream) {
     if (!h) return -1;
+    if (!h->finalized) return fail(h, -2, "smapb_infer_host: weights not finalized");
     if (B < 1 || B > h->max_batch) return fail(h, -1, "smapb_infer_host: B outside [1, max_batch]");
     cudaSetDevice(h->device);
     cudaStream_t st = stream ? (cudaStream_t)stream : h->own_stream;
-    stream = (void*)st;
+    if (!stream) {
+        int rc0 = legacy_enter(h);
+        if (rc0) return rc0;
+    }
     CK(cudaMemcpyAsync(h->imgs_dev, imgs_host, (size_t)B * 3 * h->in_h * h->in_w * 4, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(h->scales_dev, scales_host, (size_t)B * SMAPB_SCALE_LEN * 8, cudaMemcpyHostToDevice, st));
-    int rc = smapb_infer_device(h, h->imgs_dev, h->scales_dev, B, do_flip, h->records_dev, stream);
+    int rc = infer_device_impl(h, h->imgs_dev, h->scales_dev, B, do_flip, 0, h->records_dev, st);
     if (rc) return rc;
     CK(cudaMemcpyAsync(records_host, h->records_dev, (size_t)B * sizeof(smapb_record), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     return 0;
 }
 
-int smapb_submit_host(smapb_handle* h, int slot, const float* imgs_host, const double* scales_host, int B, int do_flip,
-                      smapb_record* records_host) {
+static int submit_host_impl(smapb_handle* h, int slot, const float* imgs_host, const double* scales_host, int B, int do_flip,
+                            int gather, smapb_record* records_host) {
     if (!h) return -1;
+    if (!h->finalized) return fail(h, -2, "smapb_submit_host: weights not finalized");
     if (slot < 0 || slot > 1) return fail(h, -1, "smapb_submit_host: slot must be 0 or 1");
     if (B < 1 || B > h->max_batch) return fail(h, -1, "smapb_submit_host: B outside [1, max_batch]");
+    if (gather && !h->comm) return fail(h, -52, "smapb_submit_host_gather: no communicator attached");
     cudaSetDevice(h->device);
     smapb_handle::Slot& S = h->slots[slot];
     if (!S.imgs) {
@@ -1712,6 +1930,7 @@ int smapb_submit_host(smapb_handle* h, int slot, const float* imgs_host, const d
         CK(cudaEventCreateWithFlags(&S.done, cudaEventDisableTiming));
         if (!h->copy_stream) CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
     }
+    if (gather && !S.records_all && dev_alloc(h, &S.records_all, (size_t)h->max_batch * h->comm_world)) return -10;
     // the slot's buffers are free once its previous submission has completed
     if (S.used) CK(cudaStreamWaitEvent(h->copy_stream, S.done, 0));
     CK(cudaMemcpyAsync(S.imgs, imgs_host, (size_t)B * 3 * h->in_h * h->in_w * 4, cudaMemcpyHostToDevice, h->copy_stream));
@@ -1719,12 +1938,25 @@ int smapb_submit_host(smapb_handle* h, int slot, const float* imgs_host, const d
     CK(cudaEventRecord(S.h2d, h->copy_stream));
     cudaStream_t st = h->own_stream;
     CK(cudaStreamWaitEvent(st, S.h2d, 0));
-    int rc = smapb_infer_device(h, S.imgs, S.scales, B, do_flip, S.records, (void*)st);
+    smapb_record* dst = gather ? S.records_all : S.records;
+    int rc = infer_device_impl(h, S.imgs, S.scales, B, do_flip, gather, dst, st);
     if (rc) return rc;
-    CK(cudaMemcpyAsync(records_host, S.records, (size_t)B * sizeof(smapb_record), cudaMemcpyDeviceToHost, st));
+    // gather: the records were exchanged on the device (NVLink) before this single D2H - nothing is re-uploaded
+    CK(cudaMemcpyAsync(records_host, dst, (size_t)B * (gather ? h->comm_world : 1) * sizeof(smapb_record),
+                       cudaMemcpyDeviceToHost, st));
     CK(cudaEventRecord(S.done, st));
     S.used = true;
     return 0;
+}
+
+int smapb_submit_host(smapb_handle* h, int slot, const float* imgs_host, const double* scales_host, int B, int do_flip,
+                      smapb_record* records_host) {
+    return submit_host_impl(h, slot, imgs_host, scales_host, B, do_flip, 0, records_host);
+}
+
+int smapb_submit_host_gather(smapb_handle* h, int slot, const float* imgs_host, const double* scales_host, int B, int do_flip,
+                             smapb_record* all_records_host) {
+    return submit_host_impl(h, slot, imgs_host, scales_host, B, do_flip, 1, all_records_host);
 }
 
 int smapb_wait(smapb_handle* h, int slot) {
@@ -1733,6 +1965,110 @@ int smapb_wait(smapb_handle* h, int slot) {
     cudaSetDevice(h->device);
     CK(cudaEventSynchronize(h->slots[slot].done));
     return 0;
+}
+
+// ---- multi-GPU: communicator + the one exchange step of the path ----------------------------------
+int smapb_comm_unique_id(void* id128) {
+    NcclApi& a = nccl_api();
+    if (!a.lib || !id128) return -51;
+    NcclUid id;
+    const int rc = a.GetUniqueId(&id);
+    if (rc != 0) return -50;
+    memcpy(id128, &id, 128);
+    return 0;
+}
+
+static int set_comm(smapb_handle* h, void* comm, bool owned, int rank, int world) {
+    if (world < 1 || rank < 0 || rank >= world) return fail(h, -1, "communicator: rank / world out of range");
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    if (h->comm && h->comm_owned && nccl_api().CommDestroy) nccl_api().CommDestroy(h->comm);
+    // graphs captured with the previous communicator (or without one) stay valid only for gather == 0
+    for (size_t i = 0; i < h->graphs.size();) {
+        if (h->graphs[i].gather) {
+            cudaGraphExecDestroy(h->graphs[i].exec);
+            h->graphs.erase(h->graphs.begin() + i);
+        } else {
+            i++;
+        }
+    }
+    for (auto& kv : h->eager_runs)
+        if (kv.first.second & 1) kv.second = 0;
+    h->comm = comm, h->comm_owned = owned, h->comm_rank = rank, h->comm_world = world;
+    if (h->gather_dev) cudaFree(h->gather_dev);
+    h->gather_dev = nullptr;
+    for (auto& S : h->slots) {
+        cudaFree(S.records_all);
+        S.records_all = nullptr;
+    }
+    if (dev_alloc(h, &h->gather_dev, (size_t)world * h->max_batch)) return -10;
+    return 0;
+}
+
+int smapb_comm_create(smapb_handle* h, const void* id128, int rank, int world) {
+    if (!h || !id128) return -1;
+    NcclApi& a = nccl_api();
+    if (!a.lib) return fail(h, -51, a.err.empty() ? "NCCL unavailable" : a.err);
+    cudaSetDevice(h->device);
+    NcclUid id;
+    memcpy(&id, id128, 128);
+    void* comm = nullptr;
+    const int rc = a.CommInitRank(&comm, world, id, rank);
+    if (rc != 0) return nccl_fail(h, "ncclCommInitRank", rc);
+    return set_comm(h, comm, true, rank, world);
+}
+
+int smapb_comm_attach(smapb_handle* h, void* nccl_comm, int rank, int world) {
+    if (!h || !nccl_comm) return -1;
+    NcclApi& a = nccl_api();
+    if (!a.lib) return fail(h, -51, a.err.empty() ? "NCCL unavailable" : a.err);
+    return set_comm(h, nccl_comm, false, rank, world);
+}
+
+int smapb_allgather_records(smapb_handle* h, void* nccl_comm, const smapb_record* records_dev, smapb_record* all_records_dev,
+                            int B, void* stream) {
+    if (!h || !records_dev || !all_records_dev) return -1;
+    if (B < 1) return fail(h, -1, "smapb_allgather_records: B < 1");
+    cudaSetDevice(h->device);
+    void* comm = nccl_comm ? nccl_comm : h->comm;
+    if (stream) return gather_records(h, comm, records_dev, all_records_dev, B, (cudaStream_t)stream);
+    int rc = legacy_enter(h);
+    if (!rc) rc = gather_records(h, comm, records_dev, all_records_dev, B, h->own_stream);
+    if (!rc) rc = legacy_leave(h);
+    return rc;
+}
+
+// ---- tile-shape table (process-wide) ------------------------------------------------------------------------------
+int smapb_set_tile_table(const char* text) {
+    if (!text) return -1;
+    std::lock_guard<std::mutex> lk(g_tiles_mu);
+    int n = 0;
+    const char* p = text;
+    while (*p) {
+        const char* e = strchr(p, '\n');
+        std::string line = e ? std::string(p, e - p) : std::string(p);
+        p = e ? e + 1 : p + line.size();
+        if (line.empty() || line[0] == '#') continue;
+        const size_t t1 = line.find('\t');
+        if (t1 == std::string::npos) continue;
+        int bn = 0, cg = 1;
+        if (sscanf(line.c_str() + t1 + 1, "%d\t%d", &bn, &cg) < 1 || bn <= 0) continue;
+        g_tiles[line.substr(0, t1)] = {bn, cg == 2 ? 2 : 1};
+        n++;
+    }
+    return n;
+}
+
+int smapb_get_tile_table(char* buf, int cap) {
+    std::lock_guard<std::mutex> lk(g_tiles_mu);
+    std::string out;
+    for (auto& kv : g_tiles) out += kv.first + "\t" + std::to_string(kv.second.first) + "\t" + std::to_string(kv.second.second) + "\n";
+    if (buf && cap > 0) {
+        const size_t n = std::min((size_t)cap - 1, out.size());
+        memcpy(buf, out.data(), n);
+        buf[n] = 0;
+    }
+    return (int)out.size() + 1;
 }
 
 // debug: 64-bit checksums of every plan op's output tensor after the last forward (tools/debug_ops.py)

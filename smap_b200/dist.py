@@ -40,3 +40,16 @@ def allgather_records(rec, n_frames=None, group=None):
     if all(s == bmax for s in sizes):
         return out
     return torch.cat([out[r * bmax:r * bmax + sizes[r]] for r in range(world)], 0)
+
+
+def sync_tile_table(group=None, src=0):
+    """Make every rank use rank `src`'s tile shapes for geometries the committed table does not cover: call after the
+    engines of rank `src` have built their plans (first forward) and before the other ranks build theirs - or simply
+    before any forward on all ranks when the committed table covers the workload (then this is a no-op in effect)."""
+    from . import engine
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return
+    box = [engine.get_tile_table() if dist.get_rank(group) == src else None]
+    dist.broadcast_object_list(box, src=src, group=group)
+    engine._lib.load().smapb_set_tile_table(box[0].encode())

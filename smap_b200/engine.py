@@ -2,6 +2,7 @@
 
 torch is plumbing only (device memory, streams); every kernel runs inside libsmap_b200.so."""
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -30,14 +31,46 @@ def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+TILE_TABLE_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "tiles", "b200.tsv")
+_tile_table_loaded = False
+
+
+def load_tile_table(path=TILE_TABLE_PATH):
+    """Install the committed tile-shape table (process-wide, once): every process / rank then runs every layer with the
+    same (BLOCK_N, cta_group), which makes results independent of the handle and of the rank.  Geometries the table does
+    not cover are autotuned by the library (use smap_b200.dist.sync_tile_table to share rank 0's choices)."""
+    global _tile_table_loaded
+    if _tile_table_loaded or os.environ.get("SMAPB_NO_TILE_TABLE"):
+        return 0
+    _tile_table_loaded = True
+    if not os.path.exists(path):
+        return 0
+    return _lib.load().smapb_set_tile_table(open(path, "rb").read())
+
+
+def get_tile_table():
+    """The process-wide tile table as text (committed table + whatever the autotuner added)."""
+    lib = _lib.load()
+    n = lib.smapb_get_tile_table(None, 0)
+    buf = ctypes.create_string_buffer(n)
+    lib.smapb_get_tile_table(buf, n)
+    return buf.value.decode()
+
+
 class Engine:
     """One handle per (process, device).  in_h/in_w: network input size (multiples of 32)."""
 
-    def __init__(self, device=0, max_batch=8, in_h=512, in_w=832):
+    def __init__(self, device=0, max_batch=8, in_h=512, in_w=832, stream=None):
+        """stream: None = every call runs on torch's current stream (the library bridges the legacy default stream to its
+        own non-blocking stream); a torch.cuda.Stream = the handle's calls are issued on that stream and the caller orders
+        it against other streams (pipelined use: several handles in flight, see EnginePool / bench.py)."""
         self.lib = _lib.load()
         if not torch.cuda.is_available():
             raise SmapB200Error("smap_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        load_tile_table()
         self.device = torch.device("cuda", device)
+        self.stream = stream
+        self.world, self.rank = 1, 0
         self.max_batch, self.in_h, self.in_w = max_batch, in_h, in_w
         self.h, self.w = in_h // 4, in_w // 4
         hp = ctypes.c_void_p()
@@ -58,6 +91,9 @@ class Engine:
             self.close()
         except Exception:
             pass
+
+    def _st(self):
+        return ctypes.c_void_p(self.stream.cuda_stream) if self.stream is not None else _stream()
 
     def _check(self, rc, what):
         if rc != 0:
@@ -185,13 +221,61 @@ class Engine:
         self._check(self.lib.smapb_set_refine(self._h, int(bool(enable))), "smapb_set_refine")
 
     # ---- whole path ---------------------------------------------------------------------------
-    def infer_device(self, imgs, scales, do_flip=False):
-        """imgs cuda fp32 [B,3,H,W], scales cuda f64 [B,9] -> records uint8 cuda [B, RECORD_BYTES]."""
+    def infer_device(self, imgs, scales, do_flip=False, out=None, gather=False):
+        """imgs cuda fp32 [B,3,H,W], scales cuda f64 [B,9] -> records uint8 cuda [B, RECORD_BYTES]; gather=True (after
+        init_comm): [world*B, RECORD_BYTES], all ranks' records in rank order, exchanged by ONE ncclAllGather on the same
+        stream (inside the same CUDA graph).  With an engine-owned stream the call is asynchronous with respect to torch's
+        current stream: pass `out` (preallocated) and order the streams yourself."""
         B = imgs.shape[0]
-        rec = torch.empty(B, RECORD_BYTES, dtype=torch.uint8, device=imgs.device)
-        self._check(self.lib.smapb_infer_device(self._h, _ptr(imgs.contiguous()), _ptr(scales.contiguous()), B,
-                                                int(do_flip), _ptr(rec), _stream()), "smapb_infer_device")
-        return rec
+        n = B * (self.world if gather else 1)
+        if out is None:
+            out = torch.empty(n, RECORD_BYTES, dtype=torch.uint8, device=imgs.device)
+            if self.stream is not None:
+                out.record_stream(self.stream)
+        assert out.shape[0] == n and out.is_contiguous()
+        fn = self.lib.smapb_infer_device_gather if gather else self.lib.smapb_infer_device
+        self._check(fn(self._h, _ptr(imgs.contiguous()), _ptr(scales.contiguous()), B, int(do_flip), _ptr(out), self._st()),
+                    "smapb_infer_device")
+        return out
+
+    # ---- multi-GPU ------------------------------------------------------------------------------
+    def init_comm(self, group=None):
+        """Collective over the torch.distributed group: create this handle's own NCCL communicator (rank 0 makes the
+        ncclUniqueId, torch.distributed only ships those 128 bytes).  Engines of a rank must call this in the same order
+        on every rank."""
+        import torch.distributed as dist
+
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        uid = (ctypes.c_char * 128)()
+        if self.rank == 0:
+            rc = self.lib.smapb_comm_unique_id(uid)
+            if rc != 0:
+                raise SmapB200Error("smapb_comm_unique_id failed (%d): NCCL not loadable" % rc)
+        box = [bytes(uid.raw)]
+        dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        uid = (ctypes.c_char * 128).from_buffer_copy(box[0])
+        with torch.cuda.device(self.device):
+            self._check(self.lib.smapb_comm_create(self._h, uid, self.rank, self.world), "smapb_comm_create")
+
+    def attach_torch_comm(self, group=None):
+        """Borrow torch.distributed's own ncclComm_t (ProcessGroupNCCL._comm_ptr) instead of creating one."""
+        import torch.distributed as dist
+
+        pg = group if group is not None else dist.distributed_c10d._get_default_group()
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        backend = pg._get_backend(self.device)
+        backend.eager_connect_single_device(self.device) if not backend._is_initialized() else None
+        ptr = backend._comm_ptr()
+        self._check(self.lib.smapb_comm_attach(self._h, ctypes.c_void_p(ptr), self.rank, self.world), "smapb_comm_attach")
+
+    def allgather(self, rec, out=None):
+        """rec uint8 cuda [B, RECORD_BYTES] -> [world*B, RECORD_BYTES] (smapb_allgather_records on this handle's comm)."""
+        B = rec.shape[0]
+        if out is None:
+            out = torch.empty(self.world * B, RECORD_BYTES, dtype=torch.uint8, device=rec.device)
+        self._check(self.lib.smapb_allgather_records(self._h, None, _ptr(rec.contiguous()), _ptr(out), B, self._st()),
+                    "smapb_allgather_records")
+        return out
 
     def infer_host(self, imgs, scales, do_flip=False, out=None):
         """Host buffers in, host records out (synchronous).  imgs: CPU fp32 tensor (pinned preferred) [B,3,H,W];
@@ -205,13 +289,15 @@ class Engine:
                                               _ptr(out), _stream()), "smapb_infer_host")
         return out.numpy().view(RECORD_DTYPE).reshape(B)
 
-    def submit_host(self, slot, imgs, scales, out, do_flip=False):
+    def submit_host(self, slot, imgs, scales, out, do_flip=False, gather=False):
         """Pipelined infer_host: enqueue one batch on slot 0/1 and return immediately (see smapb_submit_host).
-        imgs: pinned CPU fp32 [B,3,H,W]; scales: pinned CPU float64 [B,9]; out: pinned CPU uint8 [B, RECORD_BYTES]."""
+        imgs: pinned CPU fp32 [B,3,H,W]; scales: pinned CPU float64 [B,9]; out: pinned CPU uint8 [B, RECORD_BYTES]
+        (gather=True: [world*B, RECORD_BYTES] - the records are all-gathered on the device before the single D2H)."""
         assert not imgs.is_cuda and imgs.dtype == torch.float32 and imgs.is_contiguous()
         assert scales.dtype == torch.float64 and out.dtype == torch.uint8
-        self._check(self.lib.smapb_submit_host(self._h, slot, _ptr(imgs), _ptr(scales), imgs.shape[0], int(do_flip), _ptr(out)),
-                    "smapb_submit_host")
+        assert out.shape[0] == imgs.shape[0] * (self.world if gather else 1)
+        fn = self.lib.smapb_submit_host_gather if gather else self.lib.smapb_submit_host
+        self._check(fn(self._h, slot, _ptr(imgs), _ptr(scales), imgs.shape[0], int(do_flip), _ptr(out)), "smapb_submit_host")
 
     def wait(self, slot):
         self._check(self.lib.smapb_wait(self._h, slot), "smapb_wait")
@@ -287,16 +373,23 @@ class EnginePool:
         n = len(self.engines)
         e, slot = self.engines[t % n], (t // n) % 2
         prev = t - 2 * n
-        if prev in self._tickets:  # the slot is about to be reused: its previous occupant must be collected first
-            self.result(prev)
+        if prev in self._tickets and not self._tickets[prev][3]:
+            # the slot is about to be reused: wait for its previous occupant (its records stay in the caller's `out`
+            # buffer, so result(prev) still works afterwards)
+            pe, pslot, pout, _ = self._tickets[prev]
+            pe.wait(pslot)
+            self._tickets[prev] = (pe, pslot, pout, True)
         e.submit_host(slot, imgs, scales, out, do_flip)
-        self._tickets[t] = (e, slot, out)
+        self._tickets[t] = (e, slot, out, False)
         return t
 
     def result(self, ticket):
         """Block until the batch is done; returns its records as a numpy structured array."""
-        e, slot, out = self._tickets.pop(ticket)
-        e.wait(slot)
+        if ticket not in self._tickets:
+            raise SmapB200Error("EnginePool.result: unknown or already collected ticket %r" % (ticket,))
+        e, slot, out, done = self._tickets.pop(ticket)
+        if not done:
+            e.wait(slot)
         return out.numpy().view(RECORD_DTYPE).reshape(out.shape[0])
 
     def close(self):

@@ -55,10 +55,11 @@ def test_backbone_golden_64x96(bn, seed):
     eng.close()
 
 
-def test_backbone_832x512_vs_fp32_oracle():
+@pytest.mark.parametrize("bn", ["identity", "random"])
+def test_backbone_832x512_vs_fp32_oracle(bn):
     from smap_b200.engine import Engine
 
-    sd = smap_torch.make_state_dict(0, "identity")
+    sd = smap_torch.make_state_dict(0, bn)
     x = smap_torch.make_input(2, 512, 832, seed=1).cuda()
     ref = smap_torch.smap_forward({k: v.cuda() for k, v in sd.items()}, x)
     eng = Engine(0, max_batch=2, in_h=512, in_w=832)
@@ -69,11 +70,12 @@ def test_backbone_832x512_vs_fp32_oracle():
         assert a.shape == b.shape
         assert torch.isfinite(a).all()
         assert rel(a, b) < TOL, (name, rel(a, b))
-    # batch invariance: image 1 alone gives the same tensors
+    # batch invariance, bit for bit: image 1 alone gives the same tensors (different batch = different tile boundaries
+    # and possibly different tile shapes; every output element still accumulates the same products in the same order)
     o1 = eng.forward(x[1:2])
     torch.cuda.synchronize()
     for a, b in zip(o1, out):
-        assert rel(a[0], b[1]) < 1e-6
+        assert torch.equal(a[0], b[1])
     eng.close()
 
 

@@ -89,21 +89,36 @@ def test_conv_residual_and_post_adds_deterministic(eng, B, H, W, Cin, Cout):
         assert (y - ref).abs().max().item() / ref.abs().max().item() < 2e-5
 
 
-_TILE_CASES = [(8, 32, 52, 256, 256, 3, 1), (8, 32, 52, 1024, 256, 1, 1), (2, 16, 26, 512, 512, 3, 2)]
+_TILE_CASES = [(8, 32, 52, 256, 256, 3, 1, False), (8, 32, 52, 1024, 256, 1, 1, False), (2, 16, 26, 512, 512, 3, 2, False),
+               (4, 64, 104, 128, 512, 1, 1, True), (2, 128, 208, 256, 64, 1, 1, False)]
+_TILES = ("128,1", "64,1", "256,1", "256,2", "128,2", "64,2")
 
 
-@pytest.mark.parametrize("tile,case", [(t, c) for t in ("128,1", "64,1", "256,1") for c in _TILE_CASES] +
-                         [("256,2", c) for c in _TILE_CASES[:2]])
-def test_every_tile_shape_gives_the_same_conv(eng, monkeypatch, tile, case):
-    """The autotuner may pick any of these (BLOCK_N, CTA-group) shapes for a ring-free layer: each must be correct."""
-    B, H, W, Cin, Cout, k, stride = case
+@pytest.mark.parametrize("case", _TILE_CASES)
+def test_every_tile_shape_gives_the_same_bits(eng, monkeypatch, case):
+    """The tile table / autotuner may pick any of these (BLOCK_N, CTA-group) shapes: each must be correct AND all must
+    produce the same bits (every output element accumulates its K products in the same order whatever the tile), so that
+    results do not depend on which shape a handle, a process or a rank happens to use."""
+    B, H, W, Cin, Cout, k, stride, use_res = case
     g = torch.Generator(device="cpu").manual_seed(11)
     x = torch.randn(B, H, W, Cin, generator=g).cuda()
     w = (torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5).cuda()
     b = torch.randn(Cout, generator=g).cuda()
-    ref = F.relu(F.conv2d(x.permute(0, 3, 1, 2), w, b, stride=stride, padding=k // 2)).permute(0, 2, 3, 1)
-    monkeypatch.setenv("SMAPB_FORCE_TILE", tile)
-    y = eng.conv_test(x, w, b, stride=stride, relu=True)
-    torch.cuda.synchronize()
-    err = (y - ref).abs().max().item() / ref.abs().max().item()
-    assert err < 2e-5, "tile %s: relative error %g" % (tile, err)
+    ref = F.conv2d(x.permute(0, 3, 1, 2), w, b, stride=stride, padding=k // 2).permute(0, 2, 3, 1)
+    res = torch.randn(ref.shape, generator=g).cuda() if use_res else None
+    ref = F.relu(ref + res if use_res else ref)
+    first, n = None, 0
+    for tile in _TILES:
+        bn, cg = (int(v) for v in tile.split(","))
+        if Cout % bn or (bn == 256 and cg == 1 and use_res):  # one-CTA 128x256 tiles have no epilogue-input ring
+            continue
+        monkeypatch.setenv("SMAPB_FORCE_TILE", tile)
+        y = eng.conv_test(x, w, b, res=res, stride=stride, relu=True)
+        torch.cuda.synchronize()
+        err = (y - ref).abs().max().item() / ref.abs().max().item()
+        assert err < 2e-5, "tile %s: relative error %g" % (tile, err)
+        if first is None:
+            first = y
+        assert torch.equal(y, first), "tile %s differs from tile %s in %d elements" % (tile, _TILES[0], (y != first).sum().item())
+        n += 1
+    assert n >= 2

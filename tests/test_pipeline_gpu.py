@@ -97,13 +97,13 @@ def test_engine_pool_matches_single_engine(eng):
         if t in pool._tickets:
             pool.result(t)
     for t, (x, o) in enumerate(zip(xs, outs)):
-        # bit-identical to the synchronous call on the handle that served the ticket (tile shapes are autotuned per
-        # handle, so two handles may differ in the last bit of the backbone tensors) ...
+        # bit-identical to the synchronous call on the handle that served the ticket ...
         ref = pool.engines[t % 2].infer_host(x, scales)
         assert o.numpy().tobytes() == ref.tobytes()
-        # ... and equivalent to any other handle
+        # ... and to ANY other handle: every tile shape produces the same bits (tests/test_conv_gpu.py) and the tile
+        # table is process-wide, so results do not depend on the handle
         other = eng.infer_host(x, scales)
-        assert np.array_equal(ref["count"], other["count"])
+        assert other.tobytes() == ref.tobytes()
     pool.close()
 
 

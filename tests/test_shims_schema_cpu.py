@@ -73,3 +73,16 @@ def test_shims_match_the_reference_modules_key_for_key_and_init_for_init():
     # strict loading in both directions
     shim_refine.RefineNet().load_state_dict(ra)
     ref_refine.RefineNet().load_state_dict(rb)
+
+
+def test_oracle_and_product_generators_agree_bit_for_bit():
+    """oracle/schema_ref.py (the checker's own generators) and smap_b200/schema.py (the product's) are separate files on
+    purpose; the synthetic weights and frames they make must be the same bytes."""
+    from oracle import schema_ref
+
+    assert schema_ref.unit_specs() == schema.unit_specs()
+    for bn in ("identity", "random"):
+        a, b = schema_ref.make_state_dict(3, bn), schema.make_state_dict(3, bn)
+        assert list(a.keys()) == list(b.keys())
+        assert all(torch.equal(a[k], b[k]) for k in a)
+    assert torch.equal(schema_ref.make_input(2, 64, 96, seed=5), schema.make_input(2, 64, 96, seed=5))
