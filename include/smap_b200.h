@@ -98,6 +98,18 @@ int smapb_lift3d(smapb_handle* h, const float* bodies_dev, const int* counts_dev
                  const float* rootd_dev, const double* scales_dev, int B, float* pred2d_dev, double* pred3d_dev,
                  double* root_depth_dev, int* counts_out_dev, void* stream);
 
+/* The same with ground truth: the matching branch of register_pred (exps/stage3_root2/test_util.py:21-39) used by the
+ * reference's `generate_result` / `generate_train` test modes (exps/stage3_root2/test.py:73-95,129).  gt_roots_dev: float64
+ * [B,gmax,2] = gt_bodys[:, ROOT_IDX, :2] (network-input pixels) of the persons test.py:80-82 keeps, gt_counts_dev int32 [B].
+ * Predictions are matched to GT persons greedily by ascending root distance below 30 px (ties in row-major order); output
+ * row g belongs to GT person g (all-zero when unmatched), counts_out[b] = gt_counts[b] (0 when the frame has no
+ * prediction or no GT person - the reference skips it).  In this branch the body rows are float64 (np.zeros(..., np.float),
+ * test_util.py:35), so pred2d is float64 [B,127,15,4] as well; scales_dev carries the GT intrinsics (test.py:86-95). */
+int smapb_lift3d_gt(smapb_handle* h, const float* bodies_dev, const int* counts_dev, const float* detd_dev,
+                    const float* rootd_dev, const double* scales_dev, const double* gt_roots_dev, const int* gt_counts_dev,
+                    int gmax, int B, double* pred2d_dev, double* pred3d_dev, double* root_depth_dev, int* counts_out_dev,
+                    void* stream);
+
 /* ---- whole path -------------------------------------------------------------------------------- */
 /* Byte layout of one per-image skeleton record (the all-gather payload). */
 typedef struct smapb_record {

@@ -27,16 +27,48 @@ def default_scale(img_w=1920, img_h=1080, net_w=832, net_h=512):
                 f_x=float(img_w), f_y=float(img_w), cx=img_w / 2, cy=img_h / 2)
 
 
-def lift(bodies_hm, det_d, root_d, scale, root_n=2):
+def register_pred_gt(pred, gt_bodys, root_n=2):
+    """register_pred with ground truth (exps/stage3_root2/test_util.py:21-39): greedy one-to-one matching of GT roots to
+    predicted roots by ascending pixel distance below 30; entries are visited in ascending (distance, row-major index)
+    order - the reference finds the minimum, visits every entry equal to it in np.where order, overwrites them with 50 and
+    repeats.  Returns float64 [G,15,4]: row g = the matched prediction or zeros."""
+    root_gt = np.asarray(gt_bodys, np.float64)[:, root_n, :2]
+    root_pd = pred[:, root_n, :2]
+    diff = root_gt[:, None, :] - root_pd[None, :, :]          # float64 - float32 -> float64
+    dist = np.sqrt(diff[:, :, 0] * diff[:, :, 0] + diff[:, :, 1] * diff[:, :, 1])  # np.linalg.norm(axis=2)
+    G, P = dist.shape
+    order = sorted((dist[g, p], g * P + p) for g in range(G) for p in range(P) if dist[g, p] < 30)
+    corres = -np.ones(G, np.int64)
+    occupied = np.zeros(P, bool)
+    for _d, idx in order:
+        g, p = divmod(idx, P)
+        if corres[g] >= 0 or occupied[p]:
+            continue
+        corres[g] = p
+        occupied[p] = True
+    out = np.zeros((G, pred.shape[1], 4), np.float64)
+    for g in range(G):
+        if corres[g] >= 0:
+            out[g] = pred[corres[g]]
+    return out
+
+
+def lift(bodies_hm, det_d, root_d, scale, root_n=2, gt_bodys=None):
     """bodies_hm: float32 [P,15,4] from dapalib.connect (heat-map pixels).
     det_d: float32 [14,h,w]; root_d: float32 [h,w]; scale: dict.
     Returns (pred_2d float32 [P',15,4] with z filled in, pred_3d float64 [P',15,4],
-             root_depth float64 [P'])."""
+             root_depth float64 [P']).
+    gt_bodys (float64 [G,15,>=4], network-input pixels): the GT-matching branch of register_pred - rows follow the GT
+    order, everything downstream is float64 (np.zeros(..., np.float), test_util.py:35), pred_2d is returned as float64."""
     if len(bodies_hm) == 0:
-        return (np.zeros((0, 15, 4), np.float32), np.zeros((0, 15, 4), np.float64), np.zeros((0,), np.float64))
+        dt = np.float32 if gt_bodys is None else np.float64
+        return (np.zeros((0, 15, 4), dt), np.zeros((0, 15, 4), np.float64), np.zeros((0,), np.float64))
     pred = np.array(bodies_hm, dtype=np.float32, copy=True)
     pred[:, :, :2] *= np.float32(STRIDE)  # test.py:117 (float32 tensor op)
-    pred = pred[pred[:, root_n, 3] != 0]  # test_util.py:41
+    if gt_bodys is None:
+        pred = pred[pred[:, root_n, 3] != 0]  # test_util.py:41
+    else:
+        pred = register_pred_gt(pred, gt_bodys, root_n)
     P = len(pred)
     sc = np.float64(scale["scale"])
     fx = np.float64(scale["f_x"])

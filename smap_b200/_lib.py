@@ -18,6 +18,7 @@ EXPORTS = [
     "smapb_json_open", "smapb_json_append", "smapb_json_close", "smapb_preprocess", "smapb_preprocess_host",
     "smapb_comm_unique_id", "smapb_comm_create", "smapb_comm_attach", "smapb_allgather_records",
     "smapb_infer_device_gather", "smapb_submit_host_gather", "smapb_set_tile_table", "smapb_get_tile_table",
+    "smapb_lift3d_gt",
 ]
 
 _lib = None
@@ -53,6 +54,7 @@ def load():
     lib.smapb_assoc_extract.argtypes = [vp, vp, i32, vp, vp, vp]
     lib.smapb_assoc_connect.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp, vp]
     lib.smapb_lift3d.argtypes = [vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp]
+    lib.smapb_lift3d_gt.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, vp, vp, vp, vp, vp]
     lib.smapb_infer_device.argtypes = [vp, vp, vp, i32, i32, vp, vp]
     lib.smapb_infer_host.argtypes = [vp, vp, vp, i32, i32, vp, vp]
     lib.smapb_submit_host.argtypes = [vp, i32, vp, vp, i32, i32, vp]

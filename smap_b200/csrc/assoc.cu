@@ -46,121 +46,172 @@ __device__ __forceinline__ void stage_planes(float* dst, const float* src, uint3
     __syncthreads();
 }
 
-// ---- thread-block-cluster helpers (NMS row bands exchange their peak counts through distributed shared memory) ----
-__device__ __forceinline__ uint32_t cl_rank() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ void cl_sync() {
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ int cl_ld_s32(const int* local, uint32_t rank) {
-    uint32_t a;
-    int v;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(a) : "r"(smem_u32(local)), "r"(rank));
-    asm volatile("ld.shared::cluster.s32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
-    return v;
-}
-
 // ---------------------------------------------------------------------------------------------
-// NMS: a CLUSTER of `bands` CTAs per (image, key-point channel); CTA r owns the rows [r*rows, (r+1)*rows) of the
-// plane and stages them (+3 halo rows on each side for the 7x7 centroid) with one bulk copy - the rows are
-// contiguous in memory.  grid (bands, NJ, B), cluster (bands, 1, 1), block NMS_THREADS.
-// Peak order is raster order (required: candidate indices are part of the parity contract): warp ballots over
-// contiguous per-warp pixel segments + a block scan of the warp totals give the order inside a band, and the bands
-// exchange their totals through distributed shared memory (band r starts at the sum of bands < r).  This replaces the
-// reference's global thrust::exclusive_scan (nmsBase.cu:165-166) and works for any map size (config 5: 256x256).
+// NMS in two streaming passes (replaces nmsRegisterKernel + thrust::exclusive_scan + writeResultKernel,
+// extensions/gpu/nmsBase.cu:10-135), for any map size:
+//   nms_flag_kernel    : every warp tests 32 consecutive pixels of a plane per step (3x3 strict maximum above the
+//                        threshold, borders excluded) and stores the ballot word - one coalesced 128-byte read per step,
+//                        the 8 neighbours are only fetched for the few pixels above the threshold.  Pure HBM stream:
+//                        the planes are read exactly once, the bit masks (h*w/8 bytes per plane) are the only output.
+//   nms_compact_kernel : one CTA per (image, key-point channel) turns the bit mask into the raster-ordered peak list
+//                        (popcount prefix over contiguous runs of words = the reference's global exclusive scan restricted
+//                        to the plane, nmsBase.cu:165-166 + :57-60) and refines each peak with the 7x7 score-weighted
+//                        centroid (nmsBase.cu:84-133) - the 49 taps come from L2, which the flag pass has just filled.
+// Peak order is raster order: candidate indices are part of the parity contract.
 // ---------------------------------------------------------------------------------------------
-constexpr int NMS_THREADS = 256;
-constexpr int NMS_WARPS = NMS_THREADS / 32;
-constexpr int NMS_MAX_BANDS = 8;  // portable cluster size
+constexpr int NMSF_THREADS = 256;
+constexpr int NMSC_THREADS = 256;
+constexpr int NMSC_WARPS = NMSC_THREADS / 32;
 
-__global__ void __launch_bounds__(NMS_THREADS)
-nms_kernel(const float* __restrict__ hms, int nchan, int h, int w, int rows, float thr, float* __restrict__ peaks) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
-    int* s_cnt = reinterpret_cast<int*>(smem_raw + 8);     // this band's peak count (read by the other bands)
-    int* warp_tot = reinterpret_cast<int*>(smem_raw + 16);  // [NMS_WARPS]
-    float* tile = reinterpret_cast<float*>(smem_raw + 64);  // staged rows [r_lo, r_hi)
-    const int band = (int)cl_rank(), bands = (int)gridDim.x;
-    const int c = blockIdx.y, img = blockIdx.z;
-    const int r0 = band * rows, r1 = min(h, r0 + rows);           // owned rows (may be empty for the last bands)
-    const int r_lo = max(0, r0 - 3), r_hi = min(h, r1 + 3);       // staged rows
-    const int n_own = max(0, r1 - r0) * w;
-    const int nwords = (n_own + 31) / 32;
-    uint32_t* masks = reinterpret_cast<uint32_t*>(tile + (size_t)(rows + 6) * w);  // one ballot word per 32 owned pixels
-    const float* src = hms + ((size_t)img * nchan + c) * h * w;
-    float* out = peaks + ((size_t)img * NJ + c) * (MAXP + 1) * 3;
+// strict 3x3 maximum above the threshold, borders excluded (nmsBase.cu:24-49); v = plane[i] is already known to be > thr
+__device__ __forceinline__ bool nms_is_peak(const float* __restrict__ plane, int i, float v, int h, int w) {
+    const int y = i / w, x = i - y * w;
+    if (!(x > 0 && x < w - 1 && y > 0 && y < h - 1)) return false;
+    const float* q0 = plane + i - w;
+    const float* q2 = plane + i + w;
+    return v > __ldg(q0 - 1) && v > __ldg(q0) && v > __ldg(q0 + 1) && v > __ldg(plane + i - 1) && v > __ldg(plane + i + 1) &&
+           v > __ldg(q2 - 1) && v > __ldg(q2) && v > __ldg(q2 + 1);
+}
 
+// VEC: h*w % 128 == 0 - a warp step covers 2 x 128 consecutive pixels with two 16-byte loads per lane in flight (1 KB
+// per warp per step: enough requests outstanding to keep HBM busy; the scalar variant handles any other map size).
+template <bool VEC>
+__global__ void __launch_bounds__(NMSF_THREADS)
+nms_flag_kernel(const float* __restrict__ hms, int nchan, int B, int h, int w, float thr, uint32_t* __restrict__ masks) {
+    const int hw = h * w;
+    const int nwords = (hw + 31) / 32;
+    const int lane = threadIdx.x & 31;
+    const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
     pdl_wait();
-    if (r_hi > r_lo) stage_planes(tile, src + (size_t)r_lo * w, (uint32_t)((r_hi - r_lo) * w) * 4u, bar);
-    const float* plane = tile - (size_t)r_lo * w;  // plane[y * w + x] for staged y
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int wpw = (nwords + NMS_WARPS - 1) / NMS_WARPS;  // contiguous run of ballot words per warp
-    const int w0 = min(nwords, warp * wpw), w1 = min(nwords, w0 + wpw);
-    const int base = r0 * w;
-    int cnt = 0;
-    for (int wi = w0; wi < w1; wi++) {
-        const int i = base + wi * 32 + lane;
-        bool f = false;
-        if (wi * 32 + lane < n_own) {
-            const int y = i / w, x = i - y * w;
-            if (x > 0 && x < w - 1 && y > 0 && y < h - 1) {  // nmsBase.cu:24
-                const float v = plane[i];
-                if (v > thr) {
-                    const float* q0 = plane + i - w;
-                    const float* q2 = plane + i + w;
-                    f = v > q0[-1] && v > q0[0] && v > q0[1] && v > plane[i - 1] && v > plane[i + 1] &&
-                        v > q2[-1] && v > q2[0] && v > q2[1];
-                }
+    if (VEC) {
+        // persistent: one wave of CTAs, every warp strides over 4-group (512-pixel, 2 KB) steps with all four 16-byte
+        // loads of a lane in flight before any of them is consumed
+        constexpr int U = 4;
+        const int groups = hw / 128;                       // 128-pixel groups per plane (4 ballot words each)
+        const int total = B * NJ * groups;                 // < 2^31 for any batch that fits the workspace
+        for (int g0 = (int)warp0 * U; g0 < total; g0 += (int)nwarps * U) {
+            float4 v[U];
+            const float* pl[U];
+            int pix[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const int g = g0 + u;
+                const bool ok = g < total;
+                const int plane_id = ok ? g / groups : 0, gi = ok ? g - plane_id * groups : 0;
+                const int img = plane_id / NJ, c = plane_id - img * NJ;
+                pl[u] = hms + ((size_t)img * nchan + c) * hw;
+                pix[u] = gi * 128 + lane * 4;
+                v[u] = ok ? __ldg(reinterpret_cast<const float4*>(pl[u] + pix[u])) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const int g = g0 + u;
+                if (g >= total) break;  // warp-uniform
+                const float vv[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+                uint32_t nib = 0;
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    if (vv[k] > thr && nms_is_peak(pl[u], pix[u] + k, vv[k], h, w)) nib |= 1u << k;
+                // word j of the group = pixels [32j, 32j+32) = nibbles of lanes 8j .. 8j+7
+                uint32_t word = nib << ((lane & 7) * 4);
+                word |= __shfl_xor_sync(0xffffffffu, word, 1);
+                word |= __shfl_xor_sync(0xffffffffu, word, 2);
+                word |= __shfl_xor_sync(0xffffffffu, word, 4);
+                if ((lane & 7) == 0) masks[(size_t)g * 4 + (lane >> 3)] = word;   // nwords == 4 * groups
             }
         }
-        const uint32_t m = __ballot_sync(0xffffffffu, f);
-        if (lane == 0) masks[wi] = m;
-        cnt += __popc(m);
+    } else {
+        const long long total = (long long)B * NJ * nwords;  // ballot words of all planes
+        for (long long wd = warp0; wd < total; wd += nwarps) {
+            const int plane_id = (int)(wd / nwords), wi = (int)(wd - (long long)plane_id * nwords);
+            const int img = plane_id / NJ, c = plane_id - img * NJ;
+            const float* plane = hms + ((size_t)img * nchan + c) * hw;
+            const int i = wi * 32 + lane;
+            bool f = false;
+            if (i < hw) {
+                const float v = __ldg(plane + i);
+                f = v > thr && nms_is_peak(plane, i, v, h, w);
+            }
+            const uint32_t m = __ballot_sync(0xffffffffu, f);
+            if (lane == 0) masks[wd] = m;
+        }
     }
+    pdl_trigger();
+}
+
+__global__ void __launch_bounds__(NMSC_THREADS)
+nms_compact_kernel(const float* __restrict__ hms, int nchan, int h, int w, const uint32_t* __restrict__ masks,
+                   float* __restrict__ peaks) {
+    __shared__ int warp_tot[NMSC_WARPS];
+    const int hw = h * w;
+    const int nwords = (hw + 31) / 32;
+    const int c = blockIdx.x, img = blockIdx.y;
+    const float* plane = hms + ((size_t)img * nchan + c) * hw;
+    const uint32_t* mk = masks + ((size_t)img * NJ + c) * nwords;
+    float* out = peaks + ((size_t)img * NJ + c) * (MAXP + 1) * 3;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    pdl_wait();
+    // contiguous run of words per warp, lanes stride through the run; counts first
+    const int wpw = (nwords + NMSC_WARPS - 1) / NMSC_WARPS;
+    const int w0 = min(nwords, warp * wpw), w1 = min(nwords, w0 + wpw);
+    int cnt = 0;
+    for (int wi = w0 + lane; wi < w1; wi += 32) cnt += __popc(__ldg(mk + wi));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
     if (lane == 0) warp_tot[warp] = cnt;
     __syncthreads();
-    // exclusive prefix over the warps of this band
-    int t = (lane < NMS_WARPS) ? warp_tot[lane] : 0;
+    int t = (lane < NMSC_WARPS) ? warp_tot[lane] : 0;
     int before = (lane < warp) ? t : 0;
-    int band_total = t;
+    int total = t;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         before += __shfl_xor_sync(0xffffffffu, before, o);
-        band_total += __shfl_xor_sync(0xffffffffu, band_total, o);
+        total += __shfl_xor_sync(0xffffffffu, total, o);
     }
-    if (threadIdx.x == 0) *s_cnt = band_total;
-    cl_sync();  // every band's count is published
-    int band_off = 0, total = 0;
-    for (int r = 0; r < bands; r++) {
-        const int v = (r == band) ? band_total : cl_ld_s32(s_cnt, (uint32_t)r);
-        if (r < band) band_off += v;
-        total += v;
-    }
-    cl_sync();  // nobody leaves (or reuses s_cnt) while a peer may still read it
-    int running = band_off + before;
-    for (int wi = w0; wi < w1; wi++) {
-        const uint32_t m = masks[wi];
-        if (m == 0) continue;
-        if ((m >> lane) & 1u) {
-            const int peakIndex = running + __popc(m & ((1u << lane) - 1u));
+    // the warp walks its run 32 words at a time: an in-warp exclusive scan of the word popcounts gives every word its
+    // first peak index, then each lane expands its own word (peaks are sparse: a word rarely holds more than one)
+    int running = before;
+    for (int base = w0; base < w1 && running < MAXP; base += 32) {
+        const int wi = base + lane;
+        const uint32_t m = (wi < w1) ? __ldg(mk + wi) : 0u;
+        const int pc = __popc(m);
+        int incl = pc;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int n = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += n;
+        }
+        int peakIndex = running + incl - pc;
+        uint32_t mm = m;
+        while (mm) {
+            const int bit = __ffs(mm) - 1;
+            mm &= mm - 1;
             if (peakIndex < MAXP) {  // nmsBase.cu:92
-                const int i = base + wi * 32 + lane;
+                const int i = wi * 32 + bit;
                 const int py = i / w, px = i - py * w;
                 float xAcc = 0.f, yAcc = 0.f, sAcc = 0.f;
-                for (int dy = -3; dy <= 3; dy++) {
-                    const int y = py + dy;
-                    if (y < 0 || y >= h) continue;
-                    for (int dx = -3; dx <= 3; dx++) {
-                        const int x = px + dx;
-                        if (x < 0 || x >= w) continue;
-                        const float sc = plane[y * w + x];
+                // all 49 taps are requested before the first one is used (one memory latency per peak instead of seven:
+                // at B = 64 the planes have left L2 by the time this kernel runs), then accumulated in the reference's
+                // order (dy outer, dx inner; nmsBase.cu:101-117)
+                float tap[7][7];
+#pragma unroll
+                for (int dy = 0; dy < 7; dy++) {
+                    const int y = py + dy - 3;
+#pragma unroll
+                    for (int dx = 0; dx < 7; dx++) {
+                        const int x = px + dx - 3;
+                        tap[dy][dx] = (y >= 0 && y < h && x >= 0 && x < w) ? __ldg(plane + y * w + x) : 0.f;  // outside: skipped like s <= 0
+                    }
+                }
+#pragma unroll
+                for (int dy = 0; dy < 7; dy++) {
+#pragma unroll
+                    for (int dx = 0; dx < 7; dx++) {
+                        const float sc = tap[dy][dx];
                         if (sc > 0) {
-                            xAcc = __fmaf_rn((float)x, sc, xAcc);  // FFMA in the reference SASS
-                            yAcc = __fmaf_rn((float)y, sc, yAcc);
+                            xAcc = __fmaf_rn((float)(px + dx - 3), sc, xAcc);  // FFMA in the reference SASS
+                            yAcc = __fmaf_rn((float)(py + dy - 3), sc, yAcc);
                             sAcc = __fadd_rn(sAcc, sc);
                         }
                     }
@@ -168,21 +219,20 @@ nms_kernel(const float* __restrict__ hms, int nchan, int h, int w, int rows, flo
                 float* o = out + (peakIndex + 1) * 3;
                 o[0] = __fadd_rn(__fdiv_rn(xAcc, sAcc), 0.5f);
                 o[1] = __fadd_rn(__fdiv_rn(yAcc, sAcc), 0.5f);
-                o[2] = plane[i];
+                o[2] = __ldg(plane + i);
             }
+            peakIndex++;
         }
-        running += __popc(m);
+        running += __shfl_sync(0xffffffffu, incl, 31);
     }
-    if (band == 0) {
-        const int count = total < MAXP ? total : MAXP;
-        if (threadIdx.x == 0) {
-            out[0] = (float)count;
-            out[1] = 0.f;
-            out[2] = 0.f;
-        }
-        // deterministic tail: slots the reference leaves uninitialised are zeroed
-        for (int k = (count + 1) * 3 + threadIdx.x; k < (MAXP + 1) * 3; k += NMS_THREADS) out[k] = 0.f;
+    const int count = total < MAXP ? total : MAXP;
+    if (threadIdx.x == 0) {
+        out[0] = (float)count;
+        out[1] = 0.f;
+        out[2] = 0.f;
     }
+    // deterministic tail: slots the reference leaves uninitialised are zeroed
+    for (int k = (count + 1) * 3 + threadIdx.x; k < (MAXP + 1) * 3; k += NMSC_THREADS) out[k] = 0.f;
     pdl_trigger();
 }
 
@@ -192,8 +242,10 @@ nms_kernel(const float* __restrict__ hms, int nchan, int h, int w, int rows, flo
 // ---------------------------------------------------------------------------------------------
 constexpr int PAF_THREADS = 1024;
 
-__device__ __forceinline__ float paf_process(float ax, float ay, float bx, float by, const float* __restrict__ mapX,
-                                             const float* __restrict__ mapY, int w, int h, float near_thr) {
+// `sample(idx, px, py)` returns the two PAF components at pixel idx (shared memory, peer shared memory or global memory)
+template <typename Sampler>
+__device__ __forceinline__ float paf_process(float ax, float ay, float bx, float by, const Sampler& sample, int w, int h,
+                                             float near_thr) {
     const float dx = __fsub_rn(bx, ax);
     const float dy = __fsub_rn(by, ay);
     const float dmax = fmaxf(fabsf(dx), fabsf(dy));
@@ -213,11 +265,12 @@ __device__ __forceinline__ float paf_process(float ax, float ay, float bx, float
             mX = min(w - 1, mX);
             mY = min(h - 1, mY);
             // the reference applies no lower clamp (coordinates are >= 0.5 by construction); clamp to keep
-            // the shared-memory access in range for adversarial inputs without changing valid results
+            // the access in range for adversarial inputs without changing valid results
             mX = max(0, mX);
             mY = max(0, mY);
-            const int idx = mY * w + mX;
-            const float score = __fmaf_rn(ux, mapX[idx], __fmul_rn(uy, mapY[idx]));
+            float px, py;
+            sample(mY * w + mX, px, py);
+            const float score = __fmaf_rn(ux, px, __fmul_rn(uy, py));
             if (score > 0.05f) {
                 sum = __fadd_rn(sum, score);
                 count++;
@@ -228,6 +281,27 @@ __device__ __forceinline__ float paf_process(float ax, float ay, float bx, float
     }
     return -1.f;
 }
+
+struct PafSamplerPlanes {  // both planes behind ordinary pointers (shared or global memory)
+    const float* x;
+    const float* y;
+    __device__ __forceinline__ void operator()(int idx, float& px, float& py) const {
+        px = x[idx];
+        py = y[idx];
+    }
+};
+struct PafSamplerPair {  // own plane in this CTA's shared memory, the other one in the cluster peer's (DSMEM)
+    const float* own;
+    uint32_t peer;  // shared::cluster address of the peer's plane
+    bool own_is_x;
+    __device__ __forceinline__ void operator()(int idx, float& px, float& py) const {
+        const float a = own[idx];
+        float b;
+        asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(b) : "r"(peer + 4u * (uint32_t)idx));
+        px = own_is_x ? a : b;
+        py = own_is_x ? b : a;
+    }
+};
 
 // STAGED: both planes fit in shared memory (the parity configuration 128x208: 213 KB) and are staged once; otherwise
 // (larger maps, e.g. 256x256 at a 1024x1024 input) the line integrals gather straight from global memory / L2.
@@ -267,7 +341,7 @@ paf_kernel(const float* __restrict__ hms, int nchan, int h, int w, const float* 
         for (int p = threadIdx.x; p < npairs; p += PAF_THREADS) {
             const int a = p / nB, b = p - a * nB;
             out[a * MAXP + b] = paf_process(pk[2 * a], pk[2 * a + 1], pk[2 * (MAXP + 1) + 2 * b],
-                                            pk[2 * (MAXP + 1) + 2 * b + 1], mapX, mapX + hw, w, h, near_thr);
+                                            pk[2 * (MAXP + 1) + 2 * b + 1], PafSamplerPlanes{mapX, mapX + hw}, w, h, near_thr);
         }
     }
     if (dense_fill) {  // pafScoreKernel writes -1 outside nA x nB; only the extract() API needs it
@@ -276,6 +350,75 @@ paf_kernel(const float* __restrict__ hms, int nchan, int h, int w, const float* 
             if (a >= nA || b >= nB) out[p] = -1.f;
         }
     }
+    pdl_trigger();
+}
+
+// CTA-PAIR variant (the parity configuration): a cluster of two CTAs per (image, limb); CTA 0 stages the x plane, CTA 1 the
+// y plane (106 KB each instead of 213 KB in one CTA), every thread reads its own plane from local shared memory and the
+// other component from the peer through distributed shared memory.  Two such CTAs fit on an SM, so one CTA's bulk copy
+// runs under the other's scoring - with a single 213 KB CTA per SM the copy engine idles while pairs are scored and the
+// SM idles while the planes arrive.
+constexpr int PAFP_THREADS = 512;
+__device__ __forceinline__ uint32_t cl_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cl_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(PAFP_THREADS, 2)
+paf_pair_kernel(const float* __restrict__ hms, int nchan, int h, int w, const float* __restrict__ peaks,
+                float* __restrict__ scores, int dense_fill) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int hw = h * w;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
+    float* pk = reinterpret_cast<float*>(smem_raw + 16);  // [2][MAXP+1][2]
+    float* plane = pk + 4 * (MAXP + 1);                   // [hw]: x (rank 0) or y (rank 1) component
+    const uint32_t rank = cl_rank();
+    const int l = blockIdx.x >> 1, img = blockIdx.y;
+    const int partA = c_joint_pairs[2 * l], partB = c_joint_pairs[2 * l + 1];
+    const float* pA = peaks + ((size_t)img * NJ + partA) * (MAXP + 1) * 3;
+    const float* pB = peaks + ((size_t)img * NJ + partB) * (MAXP + 1) * 3;
+    float* out = scores + ((size_t)img * NL + l) * MAXP * MAXP;
+
+    pdl_wait();
+    const int nA = (int)pA[0], nB = (int)pB[0];
+    const bool work = nA > 0 && nB > 0;  // identical in both CTAs of the pair
+    if (work) {
+        const float* src = hms + ((size_t)img * nchan + NJ + 2 * l + rank) * hw;
+        stage_planes(plane, src, (uint32_t)hw * 4u, bar);
+        for (int i = threadIdx.x; i < nA; i += PAFP_THREADS) {
+            pk[2 * i] = pA[3 * (i + 1)];
+            pk[2 * i + 1] = pA[3 * (i + 1) + 1];
+        }
+        for (int i = threadIdx.x; i < nB; i += PAFP_THREADS) {
+            pk[2 * (MAXP + 1) + 2 * i] = pB[3 * (i + 1)];
+            pk[2 * (MAXP + 1) + 2 * i + 1] = pB[3 * (i + 1) + 1];
+        }
+    }
+    cl_sync();  // both planes are in place (and pk is visible inside this CTA)
+    if (work) {
+        uint32_t peer;
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(peer) : "r"(smem_u32(plane)), "r"(rank ^ 1u));
+        const PafSamplerPair sampler{plane, peer, rank == 0};
+        const float near_thr = __fdiv_rn(__fsqrt_rn((float)(w * h)), 150.f);
+        const int npairs = nA * nB;
+        // the two CTAs take alternate candidate pairs
+        for (int p = 2 * threadIdx.x + (int)rank; p < npairs; p += 2 * PAFP_THREADS) {
+            const int a = p / nB, b = p - a * nB;
+            out[a * MAXP + b] = paf_process(pk[2 * a], pk[2 * a + 1], pk[2 * (MAXP + 1) + 2 * b],
+                                            pk[2 * (MAXP + 1) + 2 * b + 1], sampler, w, h, near_thr);
+        }
+    }
+    if (dense_fill) {  // pafScoreKernel writes -1 outside nA x nB; only the extract() API needs it
+        for (int p = 2 * threadIdx.x + (int)rank; p < MAXP * MAXP; p += 2 * PAFP_THREADS) {
+            const int a = p / MAXP, b = p - a * MAXP;
+            if (a >= nA || b >= nB) out[p] = -1.f;
+        }
+    }
+    cl_sync();  // the peer may still be reading this CTA's plane
     pdl_trigger();
 }
 
@@ -628,8 +771,8 @@ group_kernel(const float* __restrict__ peaks, const float* __restrict__ scores, 
 // ---------------------------------------------------------------------------------------------
 constexpr int LIFT_THREADS = 256;
 
+// numpy.linspace(start, stop, 10) in the dtype of its inputs: y = i*step + start (two roundings), last = stop
 __device__ __forceinline__ float np_linspace10(float start, float stop, int i) {
-    // numpy.linspace(start, stop, 10) in float32: y = i*step + start (two roundings), last = stop
     if (i == 9) return stop;
     const float delta = __fsub_rn(stop, start);
     const float step = __fdiv_rn(delta, 9.f);
@@ -640,20 +783,46 @@ __device__ __forceinline__ float np_linspace10(float start, float stop, int i) {
         y = __fmul_rn((float)i, step);
     return __fadd_rn(y, start);
 }
+__device__ __forceinline__ double np_linspace10(double start, double stop, int i) {
+    if (i == 9) return stop;
+    const double delta = __dsub_rn(stop, start);
+    const double step = __ddiv_rn(delta, 9.0);
+    double y;
+    if (step == 0.0)
+        y = __dmul_rn(__ddiv_rn((double)i, 9.0), delta);
+    else
+        y = __dmul_rn((double)i, step);
+    return __dadd_rn(y, start);
+}
+// a float64 intermediate stored into a column of the body array (float32 rounds, float64 keeps)
+__device__ __forceinline__ void store_col(float& dst, double v) { dst = __double2float_rn(v); }
+__device__ __forceinline__ void store_col(double& dst, double v) { dst = v; }
+__device__ __forceinline__ int rint_to_int(float v) { return (int)rintf(v); }
+__device__ __forceinline__ int rint_to_int(double v) { return (int)rint(v); }
 
+// T = float : register_pred without ground truth (test_util.py:41) - float32 body rows, the run_inference mode.
+// T = double: register_pred WITH ground truth (test_util.py:21-39) - rows follow the GT order and are float64
+//             (np.zeros(..., np.float), test_util.py:35), so every float32 rounding of the other branch disappears.
+template <typename T>
 __global__ void __launch_bounds__(LIFT_THREADS, 1)
 lift_kernel(const float* __restrict__ bodies, const int* __restrict__ counts, const float* __restrict__ det_d,
             const float* __restrict__ root_d, const double* __restrict__ scales, int h, int w, int root_n,
-            float* __restrict__ pred2d_base, double* __restrict__ pred3d_base, double* __restrict__ root_depth_base,
-            int* __restrict__ counts_out, long long s2d, long long s3d, long long srd, long long scnt) {
-    __shared__ float s_b[MAXP][NJ][4];
-    __shared__ double s_dz[MAXP][NL];
-    __shared__ int s_keep[MAXP];
+            T* __restrict__ pred2d_base, double* __restrict__ pred3d_base, double* __restrict__ root_depth_base,
+            int* __restrict__ counts_out, long long s2d, long long s3d, long long srd, long long scnt,
+            const double* __restrict__ gt_roots, const int* __restrict__ gt_counts, int gmax, double* __restrict__ dist_ws) {
+    extern __shared__ __align__(16) unsigned char lift_smem[];
+    typedef T BodyRow[NJ][4];
+    BodyRow* s_b = reinterpret_cast<BodyRow*>(lift_smem);                                   // [MAXP][NJ][4]
+    double(*s_dz)[NL] = reinterpret_cast<double(*)[NL]>(lift_smem + sizeof(T) * MAXP * NJ * 4);  // [MAXP][NL]
+    int* s_keep = reinterpret_cast<int*>(lift_smem + sizeof(T) * MAXP * NJ * 4 + sizeof(double) * MAXP * NL);  // [MAXP]
     __shared__ int s_np;
+    __shared__ double s_red_v[LIFT_THREADS / 32];
+    __shared__ int s_red_i[LIFT_THREADS / 32];
+    __shared__ unsigned char s_occ[MAXP];
     const int img = blockIdx.x, tid = threadIdx.x;
     const int hw = h * w;
     // per-image output slices (strides in elements: natural layout or smapb_record fields)
-    float* pred2d = pred2d_base + (size_t)img * s2d;
+    T* pred2d = pred2d_base + (size_t)img * s2d;
     double* pred3d = pred3d_base + (size_t)img * s3d;
     double* root_depth = root_depth_base + (size_t)img * srd;
     pdl_wait();
@@ -662,21 +831,75 @@ lift_kernel(const float* __restrict__ bodies, const int* __restrict__ counts, co
     const float* dd = det_d + (size_t)img * NL * hw;
     const float* rd = root_d + (size_t)img * hw;
     const double* sc = scales + (size_t)img * 9;  // scale, img_w, img_h, net_w, net_h, fx, fy, cx, cy
-    if (tid == 0) {  // register_pred without GT (test_util.py:41): keep persons whose root score != 0
-        int n = 0;
-        for (int p = 0; p < P; p++)
-            if (b[(p * NJ + root_n) * 4 + 3] != 0.f) s_keep[n++] = p;
-        s_np = n;
+    if (gt_roots == nullptr) {
+        if (tid == 0) {  // register_pred without GT (test_util.py:41): keep persons whose root score != 0
+            int n = 0;
+            for (int p = 0; p < P; p++)
+                if (b[(p * NJ + root_n) * 4 + 3] != 0.f) s_keep[n++] = p;
+            s_np = n;
+        }
+        __syncthreads();
+    } else {
+        // register_pred with GT (test_util.py:21-39): distance matrix of GT roots x predicted roots, then the entries
+        // below 30 px are visited in ascending (distance, row-major index) order - the reference takes the minimum, walks
+        // all entries equal to it in np.where order, overwrites them with 50 and repeats - and a pair is made when both
+        // its GT person and its prediction are still free.
+        const int G = min(gt_counts[img], min(gmax, MAXP));
+        const bool skip = (P == 0) || (G <= 0);  // no prediction: empty result (:19-20); no GT person: frame skipped (test.py:83-84)
+        double* D = dist_ws + (size_t)img * MAXP * MAXP;
+        const double* gr = gt_roots + (size_t)img * gmax * 2;
+        if (!skip) {
+            for (int i = tid; i < G * P; i += LIFT_THREADS) {
+                const int g = i / P, p = i - g * P;
+                const float px = __fmul_rn(b[(p * NJ + root_n) * 4 + 0], 4.f), py = __fmul_rn(b[(p * NJ + root_n) * 4 + 1], 4.f);
+                const double dx = __dsub_rn(gr[2 * g], (double)px), dy = __dsub_rn(gr[2 * g + 1], (double)py);
+                D[i] = __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));  // np.linalg.norm(axis=2)
+            }
+            for (int g = tid; g < G; g += LIFT_THREADS) s_keep[g] = -1;
+            for (int p = tid; p < P; p += LIFT_THREADS) s_occ[p] = 0;
+        }
+        __syncthreads();
+        while (!skip) {
+            double bv = 1e300;
+            int bi = 0x7fffffff;
+            for (int i = tid; i < G * P; i += LIFT_THREADS) {
+                const double v = D[i];
+                if (v < 30.0 && (v < bv || (v == bv && i < bi))) bv = v, bi = i;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (ov < bv || (ov == bv && oi < bi)) bv = ov, bi = oi;
+            }
+            if ((tid & 31) == 0) s_red_v[tid >> 5] = bv, s_red_i[tid >> 5] = bi;
+            __syncthreads();
+            bv = s_red_v[0], bi = s_red_i[0];
+            for (int k = 1; k < LIFT_THREADS / 32; k++)
+                if (s_red_v[k] < bv || (s_red_v[k] == bv && s_red_i[k] < bi)) bv = s_red_v[k], bi = s_red_i[k];
+            if (bi == 0x7fffffff) break;  // uniform: np.min(distance_array) >= 30
+            if (tid == 0) {
+                const int g = bi / P, p = bi - g * P;
+                D[bi] = 50.0;
+                if (s_keep[g] < 0 && !s_occ[p]) s_keep[g] = p, s_occ[p] = 1;
+            }
+            __syncthreads();  // D / s_keep / s_occ updates visible; s_red reusable
+        }
+        if (tid == 0) s_np = skip ? 0 : G;
+        __syncthreads();
     }
-    __syncthreads();
     const int NP = s_np;
     for (int i = tid; i < NP * NJ; i += LIFT_THREADS) {
         const int p = i / NJ, j = i - p * NJ;
+        if (s_keep[p] < 0) {  // unmatched GT person: zero row (test_util.py:35)
+            s_b[p][j][0] = s_b[p][j][1] = s_b[p][j][2] = s_b[p][j][3] = (T)0;
+            continue;
+        }
         const float* s = b + (s_keep[p] * NJ + j) * 4;
-        s_b[p][j][0] = __fmul_rn(s[0], 4.f);  // test.py:117
-        s_b[p][j][1] = __fmul_rn(s[1], 4.f);
-        s_b[p][j][2] = s[2];
-        s_b[p][j][3] = s[3];
+        s_b[p][j][0] = (T)__fmul_rn(s[0], 4.f);  // test.py:117 (float32 tensor op, then widened in the GT branch)
+        s_b[p][j][1] = (T)__fmul_rn(s[1], 4.f);
+        s_b[p][j][2] = (T)s[2];
+        s_b[p][j][3] = (T)s[3];
     }
     __syncthreads();
     // numpy percentile constants (method 'linear'): virtual index (n-1)*q, gamma = frac
@@ -691,8 +914,8 @@ lift_kernel(const float* __restrict__ bodies, const int* __restrict__ counts, co
             float v[10];
 #pragma unroll
             for (int t = 0; t < 10; t++) {
-                const int xx = (int)rintf(np_linspace10(s_b[p][ja][0], s_b[p][jb][0], t));
-                const int yy = (int)rintf(np_linspace10(s_b[p][ja][1], s_b[p][jb][1], t));
+                const int xx = rint_to_int(np_linspace10(s_b[p][ja][0], s_b[p][jb][0], t));
+                const int yy = rint_to_int(np_linspace10(s_b[p][ja][1], s_b[p][jb][1], t));
                 const int hx = min(w - 1, max(0, xx >> 2)), hy = min(h - 1, max(0, yy >> 2));
                 v[t] = dd[(size_t)k * hw + hy * w + hx];
             }
@@ -738,13 +961,13 @@ lift_kernel(const float* __restrict__ bodies, const int* __restrict__ counts, co
             const int ry = (int)s_b[p][root_n][1], rx = (int)s_b[p][root_n][0];
             const float r = rd[min(h - 1, max(0, ry >> 2)) * w + min(w - 1, max(0, rx >> 2))];
             rdep = __dmul_rn(__dmul_rn((double)r, sc[0]), sc[5]);  // test_util.py:66
-            // chain_bones (test_util.py:45-57): float32 column written in place
-            s_b[p][2][2] = 0.f;
-            s_b[p][0][2] = __double2float_rn(__dsub_rn((double)s_b[p][2][2], s_dz[p][1]));
-            s_b[p][1][2] = __double2float_rn(__dadd_rn((double)s_b[p][0][2], s_dz[p][0]));
+            // chain_bones (test_util.py:45-57): column written in place (float32 rows round, float64 rows do not)
+            s_b[p][2][2] = (T)0;
+            store_col(s_b[p][0][2], __dsub_rn((double)s_b[p][2][2], s_dz[p][1]));
+            store_col(s_b[p][1][2], __dadd_rn((double)s_b[p][0][2], s_dz[p][0]));
             for (int k = 2; k < NL; k++) {
                 const int ja = c_joint_pairs[2 * k], jb = c_joint_pairs[2 * k + 1];
-                s_b[p][jb][2] = __double2float_rn(__dadd_rn((double)s_b[p][ja][2], s_dz[p][k]));
+                store_col(s_b[p][jb][2], __dadd_rn((double)s_b[p][ja][2], s_dz[p][k]));
             }
         }
         root_depth[p] = rdep;
@@ -752,20 +975,21 @@ lift_kernel(const float* __restrict__ bodies, const int* __restrict__ counts, co
         const double s = sc[0];
         const double offx = __ddiv_rn(__dsub_rn(__ddiv_rn(sc[3], s), sc[1]), 2.0);
         const double offy = __ddiv_rn(__dsub_rn(__ddiv_rn(sc[4], s), sc[2]), 2.0);
-        const bool has_root = s_b[p][root_n][3] != 0.f;
+        const bool has_root = s_b[p][root_n][3] != (T)0;
         for (int j = 0; j < NJ; j++) {
-            float* o2 = pred2d + ((size_t)p * NJ + j) * 4;
+            T* o2 = pred2d + ((size_t)p * NJ + j) * 4;
             o2[0] = s_b[p][j][0];
             o2[1] = s_b[p][j][1];
             o2[2] = s_b[p][j][2];
             o2[3] = s_b[p][j][3];
             double* o3 = pred3d + ((size_t)p * NJ + j) * 4;
             double X = 0, Y = 0, Z = 0;
-            const float score = s_b[p][j][3];
-            if (has_root && score != 0.f) {
-                const float bx = __double2float_rn(__dsub_rn(__ddiv_rn((double)s_b[p][j][0], s), offx));
-                const float by = __double2float_rn(__dsub_rn(__ddiv_rn((double)s_b[p][j][1], s), offy));
-                const float bz = __double2float_rn(__dadd_rn((double)s_b[p][j][2], rdep));
+            const T score = s_b[p][j][3];
+            if (has_root && score != (T)0) {
+                T bx, by, bz;
+                store_col(bx, __dsub_rn(__ddiv_rn((double)s_b[p][j][0], s), offx));
+                store_col(by, __dsub_rn(__ddiv_rn((double)s_b[p][j][1], s), offy));
+                store_col(bz, __dadd_rn((double)s_b[p][j][2], rdep));
                 const double d = (double)bz;
                 X = __ddiv_rn(__dmul_rn(__dsub_rn((double)bx, sc[7]), d), sc[5]);
                 Y = __ddiv_rn(__dmul_rn(__dsub_rn((double)by, sc[8]), d), sc[6]);
@@ -779,7 +1003,7 @@ lift_kernel(const float* __restrict__ bodies, const int* __restrict__ counts, co
     }
     // zero the unused tail of the fixed-stride record (all-gather payload must be deterministic)
     for (int i = NP * NJ * 4 + tid; i < MAXP * NJ * 4; i += LIFT_THREADS) {
-        pred2d[i] = 0.f;
+        pred2d[i] = (T)0;
         pred3d[i] = 0.0;
     }
     for (int i = NP + tid; i < MAXP; i += LIFT_THREADS) root_depth[i] = 0.0;
@@ -793,34 +1017,30 @@ lift_kernel(const float* __restrict__ bodies, const int* __restrict__ counts, co
 // ---------------------------------------------------------------------------------------------
 // host launchers
 // ---------------------------------------------------------------------------------------------
-static int nms_bands(int h) {
-    const int b = (h + 31) / 32;
-    return b < 1 ? 1 : (b > NMS_MAX_BANDS ? NMS_MAX_BANDS : b);
-}
-static int nms_rows(int h) { return (h + nms_bands(h) - 1) / nms_bands(h); }
-static size_t nms_smem(int h, int w) {
-    const int rows = nms_rows(h);
-    return 64 + (size_t)(rows + 6) * w * 4 + (size_t)((rows * w + 31) / 32) * 4;
-}
 static size_t paf_pk_bytes() { return 16 + 4 * (MAXP + 1) * 4; }
 static size_t paf_smem(int h, int w) { return paf_pk_bytes() + (size_t)h * w * 8; }
-static bool paf_staged(int h, int w) { return paf_smem(h, w) <= 232448; }
+static bool paf_staged(int h, int w) { return paf_smem(h, w) <= 232448 && (h * w) % 2 == 0; }
+static size_t paf_pair_smem(int h, int w) { return paf_pk_bytes() + (size_t)h * w * 4; }
+// two CTAs of the pair variant must fit on one SM (227 KB, 1 KB reserved per CTA)
+// Measured on B200 (B = 64 crowded scenes): 78 us against 57 us for one 213 KB CTA per SM - the DSMEM reads cost more than the
+// overlap buys - so the pair variant is opt-in (SMAPB_PAF_PAIR=1) and kept for maps whose two planes do not fit one CTA.
+static bool paf_paired(int h, int w) {
+    return paf_pair_smem(h, w) <= 113 * 1024 && (h * w) % 4 == 0 && (getenv("SMAPB_PAF_PAIR") || !paf_staged(h, w));
+}
 
-// Any map size with w % 4 == 0 (16-byte bulk copies) whose NMS row band fits in shared memory; the reference hard-codes
-// 128 x 208 (extensions/association.cpp:21).
+// Any map size: NMS streams from global memory; PAF stages both planes in shared memory when they fit (w*h*8 + 2 KB
+// <= 227 KB, needs h*w % 2 == 0 for the 16-byte bulk copies) and gathers from global memory / L2 otherwise.  The reference
+// hard-codes 128 x 208 (extensions/association.cpp:21).
 int assoc_configure(int h, int w, const char** err) {
-    static const char* e_big = "association: heat-map too large (an NMS row band of h/8 + 6 rows must fit in 227 KB of shared memory)";
-    static const char* e_align = "association: w must be a multiple of 4 (16-byte bulk copies)";
-    if (w % 4 != 0 || h < 3 || w < 4) {
-        *err = e_align;
+    static const char* e_small = "association: heat-map must be at least 3 x 3";
+    if (h < 3 || w < 3) {
+        *err = e_small;
         return -1;
     }
-    if (nms_smem(h, w) > 232448) {
-        *err = e_big;
-        return -1;
-    }
-    cudaError_t e = cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nms_smem(h, w));
-    if (e == cudaSuccess && paf_staged(h, w))
+    cudaError_t e = cudaSuccess;
+    if (paf_paired(h, w))
+        e = cudaFuncSetAttribute(paf_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)paf_pair_smem(h, w));
+    else if (paf_staged(h, w))
         e = cudaFuncSetAttribute(paf_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)paf_smem(h, w));
     if (e != cudaSuccess) {
         *err = cudaGetErrorString(e);
@@ -829,24 +1049,42 @@ int assoc_configure(int h, int w, const char** err) {
     return 0;
 }
 
-cudaError_t launch_nms(const float* hms, int nchan, int B, int h, int w, float thr, float* peaks, cudaStream_t st) {
-    const int bands = nms_bands(h);
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(bands, NJ, B);
-    cfg.blockDim = dim3(NMS_THREADS);
-    cfg.dynamicSmemBytes = nms_smem(h, w);
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = bands;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, nms_kernel, hms, nchan, h, w, nms_rows(h), thr, peaks);
+size_t nms_mask_words(int B, int h, int w) { return (size_t)B * NJ * ((h * w + 31) / 32); }
+
+cudaError_t launch_nms(const float* hms, int nchan, int B, int h, int w, float thr, float* peaks, uint32_t* masks,
+                       cudaStream_t st) {
+    const long long words = (long long)nms_mask_words(B, h, w);
+    const bool vec = (h * w) % 128 == 0;
+    const long long warps_needed = vec ? (words + 15) / 16 : words;  // 16 words (VEC, 4 groups) or 1 word per warp step
+    long long blocks = (warps_needed * 32 + NMSF_THREADS - 1) / NMSF_THREADS;
+    const long long cap = vec ? 148LL * 4 : 148LL * 8 * 4;  // VEC: one persistent wave; scalar: the warps stride over the rest
+    if (blocks > cap) blocks = cap;
+    if (vec)
+        nms_flag_kernel<true><<<(unsigned)blocks, NMSF_THREADS, 0, st>>>(hms, nchan, B, h, w, thr, masks);
+    else
+        nms_flag_kernel<false><<<(unsigned)blocks, NMSF_THREADS, 0, st>>>(hms, nchan, B, h, w, thr, masks);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    nms_compact_kernel<<<dim3(NJ, B), NMSC_THREADS, 0, st>>>(hms, nchan, h, w, masks, peaks);
+    return cudaGetLastError();
 }
 cudaError_t launch_paf(const float* hms, int nchan, int B, int h, int w, const float* peaks, float* scores,
                        int dense_fill, cudaStream_t st) {
+    if (paf_paired(h, w)) {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(2 * NL, B);
+        cfg.blockDim = dim3(PAFP_THREADS);
+        cfg.dynamicSmemBytes = paf_pair_smem(h, w);
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        return cudaLaunchKernelEx(&cfg, paf_pair_kernel, hms, nchan, h, w, peaks, scores, dense_fill);
+    }
     if (paf_staged(h, w))
         paf_kernel<true><<<dim3(NL, B), PAF_THREADS, paf_smem(h, w), st>>>(hms, nchan, h, w, peaks, scores, dense_fill);
     else
@@ -858,12 +1096,39 @@ cudaError_t launch_group(const float* peaks, const float* scores, const float* r
     group_kernel<<<B, GROUP_WARPS * 32, 0, st>>>(peaks, scores, rdepth, h, w, root_idx, dist_flag, bodies, counts);
     return cudaGetLastError();
 }
+template <typename T>
+static size_t lift_smem() { return sizeof(T) * MAXP * NJ * 4 + sizeof(double) * MAXP * NL + sizeof(int) * MAXP; }
+
 cudaError_t launch_lift(const float* bodies, const int* counts, const float* det_d, const float* root_d,
                         const double* scales, int B, int h, int w, int root_n, float* pred2d, double* pred3d,
                         double* root_depth, int* counts_out, long long s2d, long long s3d, long long srd, long long scnt,
                         cudaStream_t st) {
-    lift_kernel<<<B, LIFT_THREADS, 0, st>>>(bodies, counts, det_d, root_d, scales, h, w, root_n, pred2d, pred3d,
-                                            root_depth, counts_out, s2d, s3d, srd, scnt);
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(lift_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lift_smem<float>());
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    lift_kernel<float><<<B, LIFT_THREADS, lift_smem<float>(), st>>>(bodies, counts, det_d, root_d, scales, h, w, root_n, pred2d,
+                                                                   pred3d, root_depth, counts_out, s2d, s3d, srd, scnt, nullptr,
+                                                                   nullptr, 0, nullptr);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_lift_gt(const float* bodies, const int* counts, const float* det_d, const float* root_d,
+                           const double* scales, const double* gt_roots, const int* gt_counts, int gmax, double* dist_ws, int B,
+                           int h, int w, int root_n, double* pred2d, double* pred3d, double* root_depth, int* counts_out,
+                           cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(lift_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lift_smem<double>());
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    lift_kernel<double><<<B, LIFT_THREADS, lift_smem<double>(), st>>>(bodies, counts, det_d, root_d, scales, h, w, root_n, pred2d,
+                                                                     pred3d, root_depth, counts_out, (long long)MAXP * NJ * 4,
+                                                                     (long long)MAXP * NJ * 4, MAXP, 1, gt_roots, gt_counts, gmax,
+                                                                     dist_ws);
     return cudaGetLastError();
 }
 

@@ -146,6 +146,7 @@ struct smapb_handle {
     float* scores = nullptr;
     float* bodies = nullptr;
     int* counts = nullptr;
+    uint32_t* nms_masks = nullptr;  // one ballot bit per pixel of the key-point planes
     // whole-path workspace
     float* imgs_dev = nullptr;
     float* imgs_flip = nullptr;
@@ -190,6 +191,7 @@ struct smapb_handle {
     bool comm_owned = false;
     int comm_rank = 0, comm_world = 1;
     smapb_record* gather_dev = nullptr;  // [comm_world * max_batch]
+    double* gt_dist = nullptr;           // [max_batch][127*127] distance matrices of the GT-matching lift
     bool nccl_in_graph = getenv("SMAPB_NCCL_EAGER") == nullptr;
     bool nvtx_ops = getenv("SMAPB_NVTX") != nullptr;  // one NVTX range per plan op (phase ranges are always emitted)
     bool serpentine = getenv("SMAPB_SERPENTINE") != nullptr;
@@ -1202,6 +1204,7 @@ int smapb_create(smapb_handle** out, int device, int max_batch, int in_h, int in
     rc |= dev_alloc(h, &h->scores, MB * NL * MAXP * MAXP);
     rc |= dev_alloc(h, &h->bodies, MB * MAXP * NJ * 4);
     rc |= dev_alloc(h, &h->counts, MB);
+    rc |= dev_alloc(h, &h->nms_masks, nms_mask_words(max_batch, h->h, h->w));
     rc |= dev_alloc(h, &h->imgs_dev, MB * 3 * in_h * in_w);
     rc |= dev_alloc(h, &h->hm, MB * NC2D * hw);
     rc |= dev_alloc(h, &h->detd, MB * NL * hw);
@@ -1257,7 +1260,7 @@ void smapb_destroy(smapb_handle* h) {
     cudaFree(h->stem_tc.bias_dev);
     void* ptrs[] = {h->peaks, h->scores, h->bodies, h->counts, h->imgs_dev, h->imgs_flip, h->hm, h->hm_flip, h->detd,
                     h->rootd, h->scratch_detd, h->scratch_rootd, h->scales_dev, h->records_dev, h->stem_w, h->stem_b,
-                    h->gather_dev};
+                    h->gather_dev, h->gt_dist, h->nms_masks};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (h->refine_buf) cudaFree(h->refine_buf);
@@ -1491,9 +1494,9 @@ int smapb_assoc_extract(smapb_handle* h, const float* hms, int B, float* peaks, 
     int rc = check_assoc(h, B);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    CK(launch_nms(hms, NC2D, B, h->h, h->w, 0.2f, peaks, st));
+    CK(launch_nms(hms, NC2D, B, h->h, h->w, 0.2f, peaks, h->nms_masks, st));
     CK(launch_paf(hms, NC2D, B, h->h, h->w, peaks, pair_scores, 1, st));
-    h->launches += 2;
+    h->launches += 3;
     return 0;
 }
 
@@ -1505,10 +1508,10 @@ int smapb_assoc_connect(smapb_handle* h, const float* hms, const float* rdepth, 
     if (rc) return rc;
     if (root_idx < 0 || root_idx >= NJ) return fail(h, -1, "root_idx out of range");
     cudaStream_t st = (cudaStream_t)stream;
-    CK(launch_nms(hms, NC2D, B, h->h, h->w, 0.2f, h->peaks, st));
+    CK(launch_nms(hms, NC2D, B, h->h, h->w, 0.2f, h->peaks, h->nms_masks, st));
     CK(launch_paf(hms, NC2D, B, h->h, h->w, h->peaks, h->scores, 0, st));
     CK(launch_group(h->peaks, h->scores, rdepth, B, h->h, h->w, root_idx, dist_flag, bodies, counts, st));
-    h->launches += 3;
+    h->launches += 4;
     return 0;
 }
 
@@ -1520,6 +1523,20 @@ int smapb_lift3d(smapb_handle* h, const float* bodies, const int* counts, const 
     if (B < 1) return fail(h, -1, "B < 1");
     CK(launch_lift(bodies, counts, detd, rootd, scales, B, h->h, h->w, 2, pred2d, pred3d, root_depth, counts_out,
                    (long long)MAXP * NJ * 4, (long long)MAXP * NJ * 4, MAXP, 1, (cudaStream_t)stream));
+    h->launches++;
+    return 0;
+}
+
+int smapb_lift3d_gt(smapb_handle* h, const float* bodies, const int* counts, const float* detd, const float* rootd,
+                    const double* scales, const double* gt_roots, const int* gt_counts, int gmax, int B, double* pred2d,
+                    double* pred3d, double* root_depth, int* counts_out, void* stream) {
+    if (!h || !gt_roots || !gt_counts) return -1;
+    cudaSetDevice(h->device);
+    if (B < 1 || B > h->max_batch) return fail(h, -1, "smapb_lift3d_gt: B outside [1, max_batch]");
+    if (gmax < 1) return fail(h, -1, "smapb_lift3d_gt: gmax < 1");
+    if (!h->gt_dist && dev_alloc(h, &h->gt_dist, (size_t)h->max_batch * MAXP * MAXP)) return -10;
+    CK(launch_lift_gt(bodies, counts, detd, rootd, scales, gt_roots, gt_counts, gmax, h->gt_dist, B, h->h, h->w, 2, pred2d,
+                      pred3d, root_depth, counts_out, (cudaStream_t)stream));
     h->launches++;
     return 0;
 }
@@ -1756,7 +1773,7 @@ static int infer_body(smapb_handle* h, Plan* plan, const float* imgs, const doub
     nvtxRangePushA("smapb.association");
     CK(launch_merge_scale(h->hm, do_flip ? h->hm_flip : nullptr, B, h->h, h->w, 1, st));
     prof_mark(h, PK_ELEM, st, "merge_scale");
-    CK(launch_nms(h->hm, NC2D, B, h->h, h->w, 0.2f, h->peaks, st));
+    CK(launch_nms(h->hm, NC2D, B, h->h, h->w, 0.2f, h->peaks, h->nms_masks, st));
     prof_mark(h, PK_ASSOC, st, "nms");
     CK(launch_paf(h->hm, NC2D, B, h->h, h->w, h->peaks, h->scores, 0, st));
     prof_mark(h, PK_ASSOC, st, "paf");
@@ -1772,7 +1789,7 @@ static int infer_body(smapb_handle* h, Plan* plan, const float* imgs, const doub
                    reinterpret_cast<int*>(rb + offsetof(smapb_record, count)), sizeof(smapb_record) / 4,
                    sizeof(smapb_record) / 8, sizeof(smapb_record) / 8, sizeof(smapb_record) / 4, st));
     prof_mark(h, PK_LIFT, st, "lift");
-    h->launches += 5;
+    h->launches += 6;
     if (h->refine_on) {  // refined poses replace pred3d, as save_result(pred_bodys_2d, new_pred_bodys_3d, ...) does (test.py:137-145)
         double* p3 = reinterpret_cast<double*>(rb + offsetof(smapb_record, pred3d));
         CK(launch_refine_records(h->refine_w, reinterpret_cast<float*>(rb + offsetof(smapb_record, pred2d)), p3,
@@ -1855,7 +1872,7 @@ static int infer_device_impl(smapb_handle* h, const float* imgs, const double* s
     }
     ge->stamp = ++h->graph_clock;
     CK(cudaGraphLaunch(ge->exec, st));
-    h->launches += (int64_t)plan->ops.size() * (do_flip ? 2 : 1) + 5 + (do_flip ? 1 : 0) + (h->refine_on ? 1 : 0);
+    h->launches += (int64_t)plan->ops.size() * (do_flip ? 2 : 1) + 6 + (do_flip ? 1 : 0) + (h->refine_on ? 1 : 0);
     const smapb_record* src = h->records_dev;
     if (gather) {
         if (!gather_in_graph) {  // NCCL outside the graph, still stream-ordered on the compute stream

@@ -165,6 +165,24 @@ class Engine:
                                           _ptr(rdp), _ptr(co), _stream()), "smapb_lift3d")
         return p2, p3, rdp, co
 
+    def lift_gt(self, bodies, counts, det_d, root_d, scales, gt_roots, gt_counts):
+        """Lift with ground truth (register_pred's matching branch, test_util.py:21-39).  gt_roots: float64 cuda [B,G,2]
+        (GT root joints, network-input pixels), gt_counts: int32 cuda [B].  -> pred2d f64 [B,127,15,4], pred3d f64,
+        root_depth f64 [B,127], counts int32 [B] (= gt_counts, or 0 for skipped frames); row g <-> GT person g."""
+        B = bodies.shape[0]
+        dev = bodies.device
+        p2 = torch.empty(B, MAXP, NJ, 4, device=dev, dtype=torch.float64)
+        p3 = torch.empty(B, MAXP, NJ, 4, device=dev, dtype=torch.float64)
+        rdp = torch.empty(B, MAXP, device=dev, dtype=torch.float64)
+        co = torch.empty(B, dtype=torch.int32, device=dev)
+        gt_roots = gt_roots.to(torch.float64).contiguous()
+        assert gt_roots.dim() == 3 and gt_roots.shape[0] == B and gt_roots.shape[2] == 2
+        self._check(self.lib.smapb_lift3d_gt(self._h, _ptr(bodies.contiguous()), _ptr(counts), _ptr(det_d.contiguous()),
+                                             _ptr(root_d.contiguous()), _ptr(scales.contiguous()), _ptr(gt_roots),
+                                             _ptr(gt_counts.to(torch.int32).contiguous()), gt_roots.shape[1], B, _ptr(p2), _ptr(p3),
+                                             _ptr(rdp), _ptr(co), self._st()), "smapb_lift3d_gt")
+        return p2, p3, rdp, co
+
     # ---- pre-processing ------------------------------------------------------------------------
     def preprocess(self, images, out=None):
         """images: list of uint8 BGR [H,W,3] tensors (cuda or cpu; numpy arrays are taken as host images) ->

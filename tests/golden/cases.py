@@ -56,3 +56,36 @@ def preprocess_case_image(ci):
     base = 127 + 90 * np.sin(xx / (7 + ci))[:, :, None] * np.cos(yy / (11 + ci))[:, :, None] * np.array([1, 0.7, -0.8], np.float32)
     img = base + rng.normal(0, 40, (H, W, 3))
     return np.clip(np.rint(img), 0, 255).astype(np.uint8)
+
+
+N_GT_CASES = 12
+
+
+def lift_gt_case_inputs(ci):
+    """Inputs of the GT-matching branch (exps/stage3_root2/test.py:73-95, test_util.py:21-39): the lift case `ci` plus
+    ground-truth bodies float64 [G,15,11] = (x, y, Z, vis, X, Y, Z, f_x, f_y, cx, cy) in network-input pixels.
+    GT roots are placed near predicted roots (inside and outside the 30 px gate), with exact ties, duplicates competing for
+    one prediction, and unmatched persons."""
+    b, det_d, root_d, (iw, ih) = lift_case_inputs(ci)
+    rng = np.random.default_rng(900 + ci)
+    P = len(b)
+    G = int(rng.integers(1, 7))
+    gt = np.zeros((G, 15, 11), np.float64)
+    gt[:, :, 0] = rng.uniform(0, 832, (G, 15))
+    gt[:, :, 1] = rng.uniform(0, 512, (G, 15))
+    gt[:, :, 2] = rng.uniform(100, 800, (G, 15))
+    gt[:, :, 3] = 2
+    gt[:, :, 4:7] = rng.normal(0, 100, (G, 15, 3))
+    gt[:, :, 7], gt[:, :, 8], gt[:, :, 9], gt[:, :, 10] = 1100.0 + ci, 1105.0 + ci, iw / 2 + 3.5, ih / 2 - 2.25
+    for g in range(G):
+        if P and rng.uniform() < 0.8:
+            p = int(rng.integers(0, P))
+            r = float(rng.choice([0.0, 3.0, 12.5, 29.0, 31.0, 45.0]))
+            ang = rng.uniform(0, 2 * np.pi)
+            gt[g, 2, 0] = np.float64(b[p, 2, 0]) * 4 + r * np.cos(ang)
+            gt[g, 2, 1] = np.float64(b[p, 2, 1]) * 4 + r * np.sin(ang)
+    if G >= 2 and P and ci % 3 == 0:  # two GT persons at EXACTLY the same distance from one prediction (tie order)
+        p = 0
+        gt[0, 2, :2] = (np.float64(b[p, 2, 0]) * 4 + 6.0, np.float64(b[p, 2, 1]) * 4)
+        gt[1, 2, :2] = (np.float64(b[p, 2, 0]) * 4 - 6.0, np.float64(b[p, 2, 1]) * 4)
+    return b, det_d, root_d, (iw, ih), gt

@@ -9,6 +9,8 @@ build container.  The fixtures travel to the GPU box; /root/reference does not.
                        (exps/stage3_root2/test_util.py, lib/utils/post_3d.py) driven exactly as
                        exps/stage3_root2/test.py:116-134 does, including cv2 INTER_NEAREST up-sampling.
 
+  lift_gt_cases.npz  : the same with ground truth (register_pred's matching branch, test_util.py:21-39, float64 rows).
+
 Run:  python tests/golden/make_golden.py
 """
 import os
@@ -127,6 +129,49 @@ def golden_lift():
     print("lift golden:", N_LIFT_CASES, "cases")
 
 
+def golden_lift_gt():
+    """lift_gt_cases.npz: the GT-matching branch - unmodified register_pred(pred, gt_bodys) (test_util.py:21-39; float64
+    rows in GT order) followed by generate_relZ / gen_3d_pose with the GT intrinsics of test.py:86-95."""
+    _reference_env()
+    import cv2
+    import test_util as T
+
+    from cases import N_GT_CASES, lift_gt_case_inputs
+
+    cases = {}
+    for ci in range(N_GT_CASES):
+        b, det_d, root_d, (iw, ih), gt = lift_gt_case_inputs(ci)
+        s = min(832 / iw, 512 / ih)
+        scale = {"scale": np.asarray(s), "img_width": np.asarray(iw), "img_height": np.asarray(ih),
+                 "net_width": np.asarray(832), "net_height": np.asarray(512)}
+        scale["f_x"] = gt[0, 0, 7]   # test.py:91-95 (11-column annotations)
+        scale["f_y"] = gt[0, 0, 8]
+        scale["cx"] = gt[0, 0, 9]
+        scale["cy"] = gt[0, 0, 10]
+        pb = torch.from_numpy(b.copy())
+        if len(pb) > 0:
+            pb[:, :, :2] *= 4  # test.py:117
+        pb = pb.numpy()
+        paf_up = cv2.resize(det_d.transpose(1, 2, 0), (832, 512), interpolation=cv2.INTER_NEAREST)
+        rd_up = cv2.resize(root_d, (832, 512), interpolation=cv2.INTER_NEAREST)
+        pb = T.register_pred(pb, gt)
+        if len(pb) == 0:
+            p2 = np.zeros((0, 15, 4), np.float64)
+            p3 = np.zeros((0, 15, 4), np.float64)
+            rdep = np.zeros((0,), np.float64)
+        else:
+            assert pb.dtype == np.float64 and len(pb) == len(gt)
+            rdep = T.generate_relZ(pb, paf_up, rd_up, scale)
+            p3 = T.gen_3d_pose(pb, rdep, scale)
+            p2 = pb
+        cases["c%d_pred2d" % ci] = np.asarray(p2, np.float64)
+        cases["c%d_pred3d" % ci] = np.asarray(p3, np.float64)
+        cases["c%d_rootdepth" % ci] = np.asarray(rdep, np.float64)
+    np.savez_compressed(os.path.join(HERE, "lift_gt_cases.npz"), **cases)
+    print("lift-gt golden:", N_GT_CASES, "cases; matched rows:",
+          [int((cases["c%d_pred2d" % c][:, 2, 3] != 0).sum()) for c in range(N_GT_CASES)])
+
+
 def golden_refine():
     """refine_cases.npz: outputs of the unmodified model/refinenet.py + test_util.lift_and_refine_3d_pose on the lift
     goldens (the 2D/3D poses the reference lift produced), with seeded weights."""
@@ -207,7 +252,9 @@ def golden_preprocess():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["backbone", "lift", "refine", "json", "preprocess"]
+    which = sys.argv[1:] or ["backbone", "lift", "lift_gt", "refine", "json", "preprocess"]
+    if "lift_gt" in which:
+        golden_lift_gt()
     if "preprocess" in which:
         golden_preprocess()
     if "json" in which:

@@ -45,7 +45,7 @@ def peak_sets(peaks):
     return out
 
 
-def compare_frame(p3_a, p3_b):
+def compare_frame(p3_a, p3_b):  # noqa: D103
     """max |a-b| / max|b| over persons x joints of two [P,15,4] float64 arrays of equal shape"""
     den = max(np.abs(p3_b[..., :3]).max(), 1e-12)
     return np.abs(p3_a[..., :3] - p3_b[..., :3]).max() / den
@@ -68,7 +68,8 @@ def test_full_oracle_chain_vs_fused_path_random_init(setup, capsys):
     hms_o = smap_torch.rescale_reference_cuda(hm_o.clone())
     hms_f = eng.merge_scale(hm_f.clone(), None, True)
     torch.cuda.synchronize()
-    tot = flips = same_frames = same_count = 0
+    tot = flips = same_count = 0
+    persons_o = persons_matched = 0
     worst = 0.0
     for i in range(B):
         bod_o, pk_o, _ = assoc.connect(hms_o[i].cpu().numpy(), rd_o[i, 0].cpu().numpy(), return_all=True)
@@ -79,19 +80,26 @@ def test_full_oracle_chain_vs_fused_path_random_init(setup, capsys):
         p2, p3, rdep = lift_numpy.lift(bod_o, dd_o[i].cpu().numpy(), rd_o[i, 0].cpu().numpy(), sc)
         n = int(rec["count"][i])
         same_count += int(n == len(p2))
-        if so == sf and n == len(p2):
-            # identical candidate sets: the limb assignment must be identical (same visibility pattern) and the final 3D
-            # joints must agree to 1e-3
-            ours3 = rec["pred3d"][i, :n]
-            if np.array_equal(ours3[..., 3] != 0, p3[..., 3] != 0):
-                same_frames += 1
-                worst = max(worst, compare_frame(ours3, p3))
+        # person level: a person of the oracle chain is "the same person" in the fused output when every joint was built
+        # from the same candidates (same visibility pattern, 2D positions within 0.05 input px); its 3D joints must then
+        # agree to 1e-3 of the frame's largest coordinate
+        ours2, ours3 = rec["pred2d"][i, :n], rec["pred3d"][i, :n]
+        den = max(np.abs(p3[..., :3]).max(), 1e-12) if len(p3) else 1.0
+        persons_o += len(p2)
+        for k in range(len(p2)):
+            d = np.abs(ours2[:, :, :2] - p2[k][None, :, :2]).max(axis=(1, 2)) if n else np.zeros(0)
+            vis = (ours2[:, :, 3] != 0) == (p2[k][None, :, 3] != 0) if n else np.zeros((0, 15), bool)
+            cand = [j for j in range(n) if d[j] < 0.05 and vis[j].all()]
+            if cand:
+                persons_matched += 1
+                worst = max(worst, np.abs(ours3[cand[0], :, :3] - p3[k, :, :3]).max() / den)
     rate = flips / max(tot, 1)
     with capsys.disabled():
         print("\n[e2e random-init] frames=%d candidates=%d flipped=%d (%.3f %%) person-count-equal=%d/%d "
-              "frames-with-identical-candidates-and-assignments=%d worst-3D-rel=%.2e" %
-              (B, tot, flips, 100 * rate, same_count, B, same_frames, worst))
-    assert rate < 0.02, "candidate flip rate %.4f" % rate  # noise maps: a few candidates in 10^4 sit on a decision boundary
+              "persons-built-from-identical-candidates=%d/%d worst-3D-rel-among-them=%.2e" %
+              (B, tot, flips, 100 * rate, same_count, B, persons_matched, persons_o, worst))
+    assert rate < 0.02, "candidate flip rate %.4f" % rate  # noise maps: ~1 % of the candidates sit on a decision boundary
+    assert persons_matched > 0.3 * persons_o
     assert worst < TOL_3D
 
 

@@ -40,3 +40,19 @@ def test_lift_oracle_matches_reference_functions():
         assert np.array_equal(p2, g["c%d_pred2d" % ci]), ci
         assert np.array_equal(rdep, g["c%d_rootdepth" % ci]), ci
         assert np.array_equal(p3, g["c%d_pred3d" % ci]), ci
+
+
+def test_lift_oracle_gt_branch_matches_reference_functions():
+    """register_pred with ground truth (test_util.py:21-39) + the float64 lift it implies."""
+    from cases import N_GT_CASES, lift_gt_case_inputs
+
+    g = np.load(os.path.join(G, "lift_gt_cases.npz"))
+    for ci in range(N_GT_CASES):
+        b, det_d, root_d, (iw, ih), gt = lift_gt_case_inputs(ci)
+        sc = lift_numpy.default_scale(iw, ih)
+        sc.update(f_x=gt[0, 0, 7], f_y=gt[0, 0, 8], cx=gt[0, 0, 9], cy=gt[0, 0, 10])  # test.py:91-95
+        p2, p3, rdep = lift_numpy.lift(b, det_d, root_d, sc, gt_bodys=gt)
+        assert p2.dtype == np.float64
+        assert np.array_equal(p2, g["c%d_pred2d" % ci]), ci
+        assert np.array_equal(rdep, g["c%d_rootdepth" % ci]), ci
+        assert np.array_equal(p3, g["c%d_pred3d" % ci]), ci

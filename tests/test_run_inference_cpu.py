@@ -20,3 +20,18 @@ def test_cli_reports_missing_checkpoint(tmp_path, capsys):
     rc = R.main(["-p", os.path.join(tmp_path, "nope.pth"), "--dataset_path", str(tmp_path)])
     assert rc == 1
     assert "No such checkpoint of SMAP" in capsys.readouterr().out
+
+
+def test_glob_order_option_keeps_the_reference_order(tmp_path):
+    """dataset/custom_dataset.py:16-18 concatenates one glob per extension (jpg, png, jpeg) without sorting."""
+    import glob
+
+    d = tmp_path / "data"
+    (d / "s").mkdir(parents=True)
+    for rel in ("b.png", "a.jpg", "s/c.jpeg", "s/0.jpg"):
+        (d / rel).write_bytes(b"")
+    want = []
+    for ext in ("jpg", "png", "jpeg"):
+        want.extend(glob.glob(os.path.join(str(d), "**/*." + ext), recursive=True))
+    assert R.list_images(str(d), glob_order=True) == want
+    assert sorted(want) == R.list_images(str(d))
