@@ -69,8 +69,10 @@ __device__ __forceinline__ bool nms_is_peak(const float* __restrict__ plane, int
     if (!(x > 0 && x < w - 1 && y > 0 && y < h - 1)) return false;
     const float* q0 = plane + i - w;
     const float* q2 = plane + i + w;
-    return v > __ldg(q0 - 1) && v > __ldg(q0) && v > __ldg(q0 + 1) && v > __ldg(plane + i - 1) && v > __ldg(plane + i + 1) &&
-           v > __ldg(q2 - 1) && v > __ldg(q2) && v > __ldg(q2 + 1);
+    // all eight neighbours are requested before the first comparison (no short-circuit: one memory latency, not eight)
+    const float n0 = __ldg(q0 - 1), n1 = __ldg(q0), n2 = __ldg(q0 + 1), n3 = __ldg(plane + i - 1), n4 = __ldg(plane + i + 1),
+                n5 = __ldg(q2 - 1), n6 = __ldg(q2), n7 = __ldg(q2 + 1);
+    return (v > n0) & (v > n1) & (v > n2) & (v > n3) & (v > n4) & (v > n5) & (v > n6) & (v > n7);
 }
 
 // VEC: h*w % 128 == 0 - a warp step covers 2 x 128 consecutive pixels with two 16-byte loads per lane in flight (1 KB
@@ -86,40 +88,87 @@ nms_flag_kernel(const float* __restrict__ hms, int nchan, int B, int h, int w, f
     pdl_wait();
     if (VEC) {
         // persistent: one wave of CTAs, every warp strides over 4-group (512-pixel, 2 KB) steps with all four 16-byte
-        // loads of a lane in flight before any of them is consumed
+        // loads of a lane in flight before any of them is consumed.  Pixels above the threshold (candidates) are NOT
+        // tested where they are found - a lane that meets one would stall the other 31 on eight neighbour loads, and the
+        // next lane would do the same a few instructions later: instead the warp collects the step's candidates in a small
+        // shared list and tests them side by side, one candidate per lane (one memory latency per 32 candidates).
         constexpr int U = 4;
+        __shared__ uint32_t s_words[NMSF_THREADS / 32][4 * U];
+        __shared__ int s_cand[NMSF_THREADS / 32][64];   // (u << 16) | pixel offset inside the 128-pixel group ... | k
+        __shared__ float s_val[NMSF_THREADS / 32][64];
+        const int wl = threadIdx.x >> 5;
         const int groups = hw / 128;                       // 128-pixel groups per plane (4 ballot words each)
         const int total = B * NJ * groups;                 // < 2^31 for any batch that fits the workspace
         for (int g0 = (int)warp0 * U; g0 < total; g0 += (int)nwarps * U) {
             float4 v[U];
             const float* pl[U];
-            int pix[U];
+            int gi[U];
 #pragma unroll
             for (int u = 0; u < U; u++) {
                 const int g = g0 + u;
                 const bool ok = g < total;
-                const int plane_id = ok ? g / groups : 0, gi = ok ? g - plane_id * groups : 0;
+                const int plane_id = ok ? g / groups : 0;
+                gi[u] = ok ? g - plane_id * groups : 0;
                 const int img = plane_id / NJ, c = plane_id - img * NJ;
                 pl[u] = hms + ((size_t)img * nchan + c) * hw;
-                pix[u] = gi * 128 + lane * 4;
-                v[u] = ok ? __ldg(reinterpret_cast<const float4*>(pl[u] + pix[u])) : make_float4(0.f, 0.f, 0.f, 0.f);
+                v[u] = ok ? __ldg(reinterpret_cast<const float4*>(pl[u] + gi[u] * 128 + lane * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
+            if (lane < 4 * U) s_words[wl][lane] = 0u;
+            // candidate bits of this lane: bit (u * 4 + k)
+            uint32_t cbits = 0;
 #pragma unroll
             for (int u = 0; u < U; u++) {
-                const int g = g0 + u;
-                if (g >= total) break;  // warp-uniform
                 const float vv[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
-                uint32_t nib = 0;
 #pragma unroll
                 for (int k = 0; k < 4; k++)
-                    if (vv[k] > thr && nms_is_peak(pl[u], pix[u] + k, vv[k], h, w)) nib |= 1u << k;
-                // word j of the group = pixels [32j, 32j+32) = nibbles of lanes 8j .. 8j+7
-                uint32_t word = nib << ((lane & 7) * 4);
-                word |= __shfl_xor_sync(0xffffffffu, word, 1);
-                word |= __shfl_xor_sync(0xffffffffu, word, 2);
-                word |= __shfl_xor_sync(0xffffffffu, word, 4);
-                if ((lane & 7) == 0) masks[(size_t)g * 4 + (lane >> 3)] = word;   // nwords == 4 * groups
+                    if (vv[k] > thr) cbits |= 1u << (u * 4 + k);
             }
+            __syncwarp();
+            uint32_t pending = cbits;
+            while (__any_sync(0xffffffffu, pending != 0)) {
+                // warp-wide exclusive scan of the candidate counts -> list positions; a round takes at most 64 entries
+                const int mine = __popc(pending);
+                int incl = mine;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int n = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += n;
+                }
+                int pos = incl - mine;
+                const int n_all = __shfl_sync(0xffffffffu, incl, 31);
+                uint32_t rest = pending;
+                while (rest && pos < 64) {
+                    const int bit = __ffs(rest) - 1;
+                    rest &= rest - 1;
+                    const int u = bit >> 2, k = bit & 3;
+                    s_cand[wl][pos] = (u << 16) | (lane * 4 + k);
+                    float val = 0.f;
+#pragma unroll
+                    for (int uu = 0; uu < U; uu++) {
+                        const float vv[4] = {v[uu].x, v[uu].y, v[uu].z, v[uu].w};
+#pragma unroll
+                        for (int kk = 0; kk < 4; kk++)
+                            if (uu == u && kk == k) val = vv[kk];
+                    }
+                    s_val[wl][pos] = val;
+                    pos++;
+                }
+                pending = rest;  // whatever did not fit waits for the next round
+                __syncwarp();
+                const int n_round = n_all < 64 ? n_all : 64;
+                for (int e = lane; e < n_round; e += 32) {
+                    const int ent = s_cand[wl][e];
+                    const int u = ent >> 16, off = ent & 0xffff;
+                    // pl[] / gi[] are the same in every lane: pick entry u without dynamic register indexing
+                    const float* plane = u == 0 ? pl[0] : u == 1 ? pl[1] : u == 2 ? pl[2] : pl[3];
+                    const int gidx = u == 0 ? gi[0] : u == 1 ? gi[1] : u == 2 ? gi[2] : gi[3];
+                    if (nms_is_peak(plane, gidx * 128 + off, s_val[wl][e], h, w))
+                        atomicOr(&s_words[wl][u * 4 + (off >> 5)], 1u << (off & 31));
+                }
+                __syncwarp();
+            }
+            if (lane < 4 * U && g0 + (lane >> 2) < total) masks[(size_t)g0 * 4 + lane] = s_words[wl][lane];  // nwords == 4 * groups
+            __syncwarp();
         }
     } else {
         const long long total = (long long)B * NJ * nwords;  // ballot words of all planes
@@ -290,21 +339,15 @@ struct PafSamplerPlanes {  // both planes behind ordinary pointers (shared or gl
         py = y[idx];
     }
 };
-struct PafSamplerPair {  // own plane in this CTA's shared memory, the other one in the cluster peer's (DSMEM)
-    const float* own;
-    uint32_t peer;  // shared::cluster address of the peer's plane
-    bool own_is_x;
-    __device__ __forceinline__ void operator()(int idx, float& px, float& py) const {
-        const float a = own[idx];
-        float b;
-        asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(b) : "r"(peer + 4u * (uint32_t)idx));
-        px = own_is_x ? a : b;
-        py = own_is_x ? b : a;
-    }
-};
-
 // STAGED: both planes fit in shared memory (the parity configuration 128x208: 213 KB) and are staged once; otherwise
 // (larger maps, e.g. 256x256 at a 1024x1024 input) the line integrals gather straight from global memory / L2.
+// Two restructurings were built, measured on B200 at B = 64 crowded scenes and dropped (this kernel: 55.6 us, 3.46 TB/s):
+//  * a cluster of two CTAs per item, one plane each, the other component read through distributed shared memory, so that
+//    two CTAs fit on an SM and one's copy overlaps the other's scoring: 78.5 us - 25 dependent DSMEM loads per pair;
+//  * a persistent CTA with the x and y planes in separate buffers and the scoring split in an x pass and a y pass, so that
+//    a plane is refilled while the other is in use: 57 - 60 us - the scoring of an item (IEEE sqrt / divisions of the
+//    reference, a <= 25-sample chain per pair, CTA barriers) takes ~6 us, longer than the 4.5 us its planes need at 7 TB/s
+//    (tools/probes/bw_probe.cu), so the copy engine was never the bottleneck of this kernel at 15 persons per frame.
 template <bool STAGED>
 __global__ void __launch_bounds__(PAF_THREADS, 1)
 paf_kernel(const float* __restrict__ hms, int nchan, int h, int w, const float* __restrict__ peaks,
@@ -350,75 +393,6 @@ paf_kernel(const float* __restrict__ hms, int nchan, int h, int w, const float* 
             if (a >= nA || b >= nB) out[p] = -1.f;
         }
     }
-    pdl_trigger();
-}
-
-// CTA-PAIR variant (the parity configuration): a cluster of two CTAs per (image, limb); CTA 0 stages the x plane, CTA 1 the
-// y plane (106 KB each instead of 213 KB in one CTA), every thread reads its own plane from local shared memory and the
-// other component from the peer through distributed shared memory.  Two such CTAs fit on an SM, so one CTA's bulk copy
-// runs under the other's scoring - with a single 213 KB CTA per SM the copy engine idles while pairs are scored and the
-// SM idles while the planes arrive.
-constexpr int PAFP_THREADS = 512;
-__device__ __forceinline__ uint32_t cl_rank() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ void cl_sync() {
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-
-__global__ void __launch_bounds__(PAFP_THREADS, 2)
-paf_pair_kernel(const float* __restrict__ hms, int nchan, int h, int w, const float* __restrict__ peaks,
-                float* __restrict__ scores, int dense_fill) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int hw = h * w;
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
-    float* pk = reinterpret_cast<float*>(smem_raw + 16);  // [2][MAXP+1][2]
-    float* plane = pk + 4 * (MAXP + 1);                   // [hw]: x (rank 0) or y (rank 1) component
-    const uint32_t rank = cl_rank();
-    const int l = blockIdx.x >> 1, img = blockIdx.y;
-    const int partA = c_joint_pairs[2 * l], partB = c_joint_pairs[2 * l + 1];
-    const float* pA = peaks + ((size_t)img * NJ + partA) * (MAXP + 1) * 3;
-    const float* pB = peaks + ((size_t)img * NJ + partB) * (MAXP + 1) * 3;
-    float* out = scores + ((size_t)img * NL + l) * MAXP * MAXP;
-
-    pdl_wait();
-    const int nA = (int)pA[0], nB = (int)pB[0];
-    const bool work = nA > 0 && nB > 0;  // identical in both CTAs of the pair
-    if (work) {
-        const float* src = hms + ((size_t)img * nchan + NJ + 2 * l + rank) * hw;
-        stage_planes(plane, src, (uint32_t)hw * 4u, bar);
-        for (int i = threadIdx.x; i < nA; i += PAFP_THREADS) {
-            pk[2 * i] = pA[3 * (i + 1)];
-            pk[2 * i + 1] = pA[3 * (i + 1) + 1];
-        }
-        for (int i = threadIdx.x; i < nB; i += PAFP_THREADS) {
-            pk[2 * (MAXP + 1) + 2 * i] = pB[3 * (i + 1)];
-            pk[2 * (MAXP + 1) + 2 * i + 1] = pB[3 * (i + 1) + 1];
-        }
-    }
-    cl_sync();  // both planes are in place (and pk is visible inside this CTA)
-    if (work) {
-        uint32_t peer;
-        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(peer) : "r"(smem_u32(plane)), "r"(rank ^ 1u));
-        const PafSamplerPair sampler{plane, peer, rank == 0};
-        const float near_thr = __fdiv_rn(__fsqrt_rn((float)(w * h)), 150.f);
-        const int npairs = nA * nB;
-        // the two CTAs take alternate candidate pairs
-        for (int p = 2 * threadIdx.x + (int)rank; p < npairs; p += 2 * PAFP_THREADS) {
-            const int a = p / nB, b = p - a * nB;
-            out[a * MAXP + b] = paf_process(pk[2 * a], pk[2 * a + 1], pk[2 * (MAXP + 1) + 2 * b],
-                                            pk[2 * (MAXP + 1) + 2 * b + 1], sampler, w, h, near_thr);
-        }
-    }
-    if (dense_fill) {  // pafScoreKernel writes -1 outside nA x nB; only the extract() API needs it
-        for (int p = 2 * threadIdx.x + (int)rank; p < MAXP * MAXP; p += 2 * PAFP_THREADS) {
-            const int a = p / MAXP, b = p - a * MAXP;
-            if (a >= nA || b >= nB) out[p] = -1.f;
-        }
-    }
-    cl_sync();  // the peer may still be reading this CTA's plane
     pdl_trigger();
 }
 
@@ -1020,14 +994,6 @@ lift_kernel(const float* __restrict__ bodies, const int* __restrict__ counts, co
 static size_t paf_pk_bytes() { return 16 + 4 * (MAXP + 1) * 4; }
 static size_t paf_smem(int h, int w) { return paf_pk_bytes() + (size_t)h * w * 8; }
 static bool paf_staged(int h, int w) { return paf_smem(h, w) <= 232448 && (h * w) % 2 == 0; }
-static size_t paf_pair_smem(int h, int w) { return paf_pk_bytes() + (size_t)h * w * 4; }
-// two CTAs of the pair variant must fit on one SM (227 KB, 1 KB reserved per CTA)
-// Measured on B200 (B = 64 crowded scenes): 78 us against 57 us for one 213 KB CTA per SM - the DSMEM reads cost more than the
-// overlap buys - so the pair variant is opt-in (SMAPB_PAF_PAIR=1) and kept for maps whose two planes do not fit one CTA.
-static bool paf_paired(int h, int w) {
-    return paf_pair_smem(h, w) <= 113 * 1024 && (h * w) % 4 == 0 && (getenv("SMAPB_PAF_PAIR") || !paf_staged(h, w));
-}
-
 // Any map size: NMS streams from global memory; PAF stages both planes in shared memory when they fit (w*h*8 + 2 KB
 // <= 227 KB, needs h*w % 2 == 0 for the 16-byte bulk copies) and gathers from global memory / L2 otherwise.  The reference
 // hard-codes 128 x 208 (extensions/association.cpp:21).
@@ -1038,9 +1004,7 @@ int assoc_configure(int h, int w, const char** err) {
         return -1;
     }
     cudaError_t e = cudaSuccess;
-    if (paf_paired(h, w))
-        e = cudaFuncSetAttribute(paf_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)paf_pair_smem(h, w));
-    else if (paf_staged(h, w))
+    if (paf_staged(h, w))
         e = cudaFuncSetAttribute(paf_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)paf_smem(h, w));
     if (e != cudaSuccess) {
         *err = cudaGetErrorString(e);
@@ -1070,21 +1034,6 @@ cudaError_t launch_nms(const float* hms, int nchan, int B, int h, int w, float t
 }
 cudaError_t launch_paf(const float* hms, int nchan, int B, int h, int w, const float* peaks, float* scores,
                        int dense_fill, cudaStream_t st) {
-    if (paf_paired(h, w)) {
-        cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3(2 * NL, B);
-        cfg.blockDim = dim3(PAFP_THREADS);
-        cfg.dynamicSmemBytes = paf_pair_smem(h, w);
-        cfg.stream = st;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = 2;
-        attr[0].val.clusterDim.y = 1;
-        attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        return cudaLaunchKernelEx(&cfg, paf_pair_kernel, hms, nchan, h, w, peaks, scores, dense_fill);
-    }
     if (paf_staged(h, w))
         paf_kernel<true><<<dim3(NL, B), PAF_THREADS, paf_smem(h, w), st>>>(hms, nchan, h, w, peaks, scores, dense_fill);
     else
