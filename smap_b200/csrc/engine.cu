@@ -760,6 +760,9 @@ struct PlanBuilder {
             return a;
         }
         plan->allocs.push_back(p);
+        // one-time zero fill: every element is overwritten by its producer before it is read, but the producers store
+        // through TMA (cp.async.bulk.tensor), which compute-sanitizer's initcheck does not track
+        cudaMemset(p, 0, (size_t)a.plane() * 2 * h->planes);
         a.ptr = (__nv_bfloat16*)p;
         return a;
     }
@@ -917,6 +920,7 @@ int build_plan(smapb_handle* h, int B, Plan** out_plan, int instance = 0) {
             if (cudaMalloc(&p, (size_t)s2d.plane() * 2 * h->planes) != cudaSuccess)
                 return fail(h, -10, "cudaMalloc failed for the s2d input");
             plan->allocs.push_back(p);
+            cudaMemset(p, 0, (size_t)s2d.plane() * 2 * h->planes);
             s2d.ptr = (__nv_bfloat16*)p;
             Op oc;
             oc.kind = OP_CONV;
@@ -2273,6 +2277,7 @@ int smapb_conv_test(smapb_handle* h, const float* x, const float* w, const float
     CKT(cudaMalloc(&p, (size_t)out.plane() * 2 * h->planes));
     tmp.push_back(p);
     out.ptr = (__nv_bfloat16*)p;
+    CKT(cudaMemset(p, 0, (size_t)out.plane() * 2 * h->planes));  // TMA stores are invisible to initcheck
     CKT(launch_f32_to_split(x, in.ptr, in.plane(), in.plane(), h->planes, st));
     const float* extra_src[3] = {res, post1, post2};
     Act* extra_act[3] = {&r, &p1, &p2};
