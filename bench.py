@@ -251,7 +251,7 @@ def run_ours(args):
         e = Engine(local, max_batch=B, in_h=IN_H, in_w=IN_W, stream=torch.cuda.Stream(dev))
         e.load_state_dict(sd0, precision=args.precision)
         engines.append(e)
-    gather = world > 1
+    gather = world > 1 and not os.environ.get("SMAPB_BENCH_NO_GATHER")  # (diagnostic switch: N independent replicas)
     if gather:
         for e in engines:
             e.init_comm()
@@ -278,9 +278,10 @@ def run_ours(args):
         sdist.sync_tile_table()
 
     def step_device(i):
-        # whole path + ONE ncclAllGather of the skeleton records (world > 1), all on the handle's stream / in its graph
+        # whole path + ONE ncclAllGather of the skeleton records per step (world > 1): the path on the handle's stream (CUDA
+        # graph), the exchange behind an event on the handle's gather stream, so that no rank's compute waits for a peer
         engines[i % NE].infer_device(dev_batches[i % NROT], scales_dev, do_flip=bool(args.flip), out=dev_outs[i % NE],
-                                     gather=gather)
+                                     gather=gather, defer=gather and not os.environ.get("SMAPB_BENCH_SYNC_GATHER"))
 
     DEPTH = 2 * NE  # batches in flight on the host path: two slots per handle
     host_outs = [torch.empty(NOUT, RECORD_BYTES, dtype=torch.uint8).pin_memory() for _ in range(DEPTH)]
@@ -321,16 +322,23 @@ def run_ours(args):
             e.stream.wait_event(e0)
         fn(steps)
         for e in engines:
+            if gather:
+                e.gather_sync()  # every exchange of the timed steps has completed before e1
             cur.wait_stream(e.stream)
         e1.record(cur)
         torch.cuda.synchronize()
         wall = time.perf_counter() - t0
         ms = e0.elapsed_time(e1)
+        per_rank = [ms / steps]
         if world > 1:
             t = torch.tensor([ms, wall * 1e3], device=dev, dtype=torch.float64)
+            allt = [torch.zeros_like(t) for _ in range(world)]
+            dist.all_gather(allt, t)
+            per_rank = [float(a[0]) / steps for a in allt]
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms, wall = t[0].item(), t[1].item() * 1e-3
             dist.barrier()
+        timed.per_rank = per_rank
         return ms, wall
 
     # SETUP (not warm-up, not timed): every (handle, input batch) pair the loops will use goes through its two eager
@@ -353,6 +361,7 @@ def run_ours(args):
     sampler.start()
     l0 = sum(e.launch_count() for e in engines)
     ms_dev, wall_dev = timed(run_device, args.steps)
+    per_rank_ms = timed.per_rank
     launches = sum(e.launch_count() for e in engines) - l0
     sampler.stop_flag = True
     sampler.join(timeout=2)
@@ -407,7 +416,7 @@ def run_ours(args):
             "config": {"workload": WORKLOAD, "frames_per_gpu_per_step": B, "flip_tta": int(args.flip),
                        "l2": "inputs rotate over %d distinct batches (%.0f MB) and every step streams >2 GB of activations (> 126 MB L2)"
                              % (NROT, NROT * B * 3 * IN_H * IN_W * 4 / 1e6),
-                       "parallelism": "dp%d, one ncclAllGather of skeleton records per step on the compute stream (inside the CUDA graph)" % world,
+                       "parallelism": "dp%d, one ncclAllGather of skeleton records per step (handle-owned communicator, gather stream behind an event)" % world,
                        "batches_in_flight_per_gpu": NE,
                        "setup_steps_before_warmup": n_setup,
                        "setup": "graph capture per (handle, input batch) pair; not warm-up, not timed"},
@@ -415,6 +424,7 @@ def run_ours(args):
                     "d2h_bytes_per_step": NOUT * RECORD_BYTES, "ms_per_step": 1e3 * wall_host / args.steps,
                     "batches_in_flight_per_gpu": DEPTH},
             "gpu_launches": int(launches),
+            "ms_per_step_per_rank": [round(v, 4) for v in per_rank_ms],
             "clocks": sampler.result(),
             "roofline": {"bound": "tensor", "kernel": "conv_tc_kernel (%d launches/step)" % (conv_n // prof_steps),
                          "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,

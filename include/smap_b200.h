@@ -164,6 +164,16 @@ int smapb_infer_device_gather(smapb_handle* h, const float* imgs_nchw_dev, const
                               smapb_record* all_records_dev, void* stream);
 int smapb_submit_host_gather(smapb_handle* h, int slot, const float* imgs_nchw_host, const double* scales_host, int B,
                              int do_flip, smapb_record* all_records_host);
+/* Decoupled form for streams of batches (what bench.py times at N > 1): the whole path is enqueued on `stream`, the all-gather
+ * on the handle's own gather stream behind an event - `stream` is ordered after the COMPUTE only, so a rank's compute stream
+ * never waits for its peers (measured on 2 x B200: the stream-ordered form above costs 0.4 ms per 9.1 ms step - not in the
+ * 14 us collective but in the lock-step it imposes on the ranks' two batches in flight; this form costs nothing).
+ * all_records_dev is valid once smapb_gather_sync(h, s) has made a stream s wait for the outstanding exchanges.  The records
+ * are double-buffered inside the handle: a call waits at most for the exchange issued two calls earlier.
+ * smapb_submit_host_gather uses the same side stream (its smapb_wait covers the exchange and the D2H). */
+int smapb_infer_device_gather_async(smapb_handle* h, const float* imgs_nchw_dev, const double* scales_dev, int B, int do_flip,
+                                    smapb_record* all_records_dev, void* stream);
+int smapb_gather_sync(smapb_handle* h, void* stream);
 
 /* ---- RefineNet post-processing (optional; the reference enables it with `-rp`, exps/stage3_root2/test.sh) ------- */
 /* Replaces: refine_model.load_state_dict(torch.load(path)) (exps/stage3_root2/test.py:213-214) for model/refinenet.py:

@@ -18,7 +18,7 @@ EXPORTS = [
     "smapb_json_open", "smapb_json_append", "smapb_json_close", "smapb_preprocess", "smapb_preprocess_host",
     "smapb_comm_unique_id", "smapb_comm_create", "smapb_comm_attach", "smapb_allgather_records",
     "smapb_infer_device_gather", "smapb_submit_host_gather", "smapb_set_tile_table", "smapb_get_tile_table",
-    "smapb_lift3d_gt",
+    "smapb_lift3d_gt", "smapb_infer_device_gather_async", "smapb_gather_sync",
 ]
 
 _lib = None
@@ -79,6 +79,8 @@ def load():
     lib.smapb_allgather_records.argtypes = [vp, vp, vp, vp, i32, vp]
     lib.smapb_infer_device_gather.argtypes = [vp, vp, vp, i32, i32, vp, vp]
     lib.smapb_submit_host_gather.argtypes = [vp, i32, vp, vp, i32, i32, vp]
+    lib.smapb_infer_device_gather_async.argtypes = [vp, vp, vp, i32, i32, vp, vp]
+    lib.smapb_gather_sync.argtypes = [vp, vp]
     lib.smapb_set_tile_table.argtypes = [c.c_char_p]
     lib.smapb_get_tile_table.argtypes = [c.c_char_p, i32]
     lib.smapb_json_open.argtypes = [c.POINTER(vp), c.c_char_p, c.c_char_p]

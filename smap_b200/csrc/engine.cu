@@ -127,6 +127,7 @@ struct Plan {
 struct smapb_handle {
     int device = 0, max_batch = 0, in_h = 0, in_w = 0, h = 0, w = 0;
     int sm_count = 148;
+    int sm_reserve = 0;  // SMs the persistent conv grids leave to concurrent kernels
     std::string err;
     int64_t launches = 0;
     // weights
@@ -165,7 +166,7 @@ struct smapb_handle {
         double* scales = nullptr;
         smapb_record* records = nullptr;
         smapb_record* records_all = nullptr;  // [comm_world * max_batch], gathered variant
-        cudaEvent_t h2d = nullptr, done = nullptr;
+        cudaEvent_t h2d = nullptr, done = nullptr, rec_ready = nullptr;
         bool used = false;
     } slots[2];
     cudaStream_t copy_stream = nullptr;
@@ -191,6 +192,13 @@ struct smapb_handle {
     bool comm_owned = false;
     int comm_rank = 0, comm_world = 1;
     smapb_record* gather_dev = nullptr;  // [comm_world * max_batch]
+    // decoupled exchange (smapb_infer_device_gather_async / smapb_submit_host_gather): the all-gather runs on its own stream
+    // behind an event, so a rank's compute stream never waits for its peers
+    cudaStream_t gather_stream = nullptr;
+    cudaEvent_t rec_ready[2] = {nullptr, nullptr}, gather_done[2] = {nullptr, nullptr};
+    smapb_record* rec_buf[2] = {nullptr, nullptr};  // [max_batch] each: the records of the two most recent async calls
+    bool gather_used[2] = {false, false};
+    int gather_idx = 0;
     double* gt_dist = nullptr;           // [max_batch][127*127] distance matrices of the GT-matching lift
     bool nccl_in_graph = getenv("SMAPB_NCCL_EAGER") == nullptr;
     bool nvtx_ops = getenv("SMAPB_NVTX") != nullptr;  // one NVTX range per plan op (phase ranges are always emitted)
@@ -1125,7 +1133,7 @@ int run_plan(smapb_handle* h, Plan* plan, const float* imgs, float* hm2d, float*
                 prof_mark(h, PK_STEM, st, "maxpool");
                 break;
             case OP_CONV:
-                CK(launch_conv(op.cp, op.block_n, h->nterms, h->sm_count, st, h->use_pdl, op.cg));
+                CK(launch_conv(op.cp, op.block_n, h->nterms, h->sm_count - h->sm_reserve, st, h->use_pdl, op.cg));
                 if (h->profiling) {
                     char d[160];
                     snprintf(d, sizeof d, "conv k%dx%d s%d cin%d cout%d out%dx%d bn%d cg%d tiles%d", op.cp.kh, op.cp.kw,
@@ -1201,6 +1209,10 @@ int smapb_create(smapb_handle** out, int device, int max_batch, int in_h, int in
     h->in_h = in_h, h->in_w = in_w;
     h->h = in_h / 4, h->w = in_w / 4;
     h->sm_count = prop.multiProcessorCount;
+    // SMs left free by the persistent conv grids (see smapb_comm_create): a conv CTA takes a whole SM (227 KB of shared
+    // memory), so any other resident CTA - a spinning NCCL channel, the other handle's grouping kernel - pushes one conv
+    // CTA into a second wave
+    if (getenv("SMAPB_SM_RESERVE")) h->sm_reserve = std::max(0, std::min(32, atoi(getenv("SMAPB_SM_RESERVE"))));
     const size_t hw = (size_t)h->h * h->w;
     const size_t MB = max_batch;
     int rc = 0;
@@ -1248,8 +1260,15 @@ void smapb_destroy(smapb_handle* h) {
         cudaFree(S.records_all);
         if (S.h2d) cudaEventDestroy(S.h2d);
         if (S.done) cudaEventDestroy(S.done);
+        if (S.rec_ready) cudaEventDestroy(S.rec_ready);
     }
     if (h->comm && h->comm_owned && nccl_api().CommDestroy) nccl_api().CommDestroy(h->comm);
+    if (h->gather_stream) cudaStreamDestroy(h->gather_stream);
+    for (int i = 0; i < 2; i++) {
+        if (h->rec_ready[i]) cudaEventDestroy(h->rec_ready[i]);
+        if (h->gather_done[i]) cudaEventDestroy(h->gather_done[i]);
+        cudaFree(h->rec_buf[i]);
+    }
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     if (h->aux_stream) cudaStreamDestroy(h->aux_stream);
@@ -1890,6 +1909,39 @@ static int infer_device_impl(smapb_handle* h, const float* imgs, const double* s
     return 0;
 }
 
+static int gather_side_init(smapb_handle* h) {
+    if (h->gather_stream) return 0;
+    CK(cudaStreamCreateWithFlags(&h->gather_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) {
+        CK(cudaEventCreateWithFlags(&h->rec_ready[i], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&h->gather_done[i], cudaEventDisableTiming));
+        if (dev_alloc(h, &h->rec_buf[i], (size_t)h->max_batch)) return -10;
+    }
+    return 0;
+}
+
+// Whole path on `st`, exchange on the handle's gather stream: `st` is ordered after the COMPUTE only.  all_records is valid
+// once smapb_gather_sync has made a stream wait for the exchange.  The records are double-buffered, so a call only waits for
+// the exchange issued two calls earlier.
+static int infer_device_gather_async_impl(smapb_handle* h, const float* imgs, const double* scales, int B, int do_flip,
+                                          smapb_record* all_records, cudaStream_t st) {
+    if (!h->comm) return fail(h, -52, "smapb_infer_device_gather_async: no communicator attached");
+    int rc = gather_side_init(h);
+    if (rc) return rc;
+    const int idx = h->gather_idx;
+    h->gather_idx ^= 1;
+    if (h->gather_used[idx]) CK(cudaStreamWaitEvent(st, h->gather_done[idx], 0));
+    rc = infer_device_impl(h, imgs, scales, B, do_flip, 0, h->rec_buf[idx], st);
+    if (rc) return rc;
+    CK(cudaEventRecord(h->rec_ready[idx], st));
+    CK(cudaStreamWaitEvent(h->gather_stream, h->rec_ready[idx], 0));
+    rc = gather_records(h, h->comm, h->rec_buf[idx], all_records, B, h->gather_stream);
+    if (rc) return rc;
+    CK(cudaEventRecord(h->gather_done[idx], h->gather_stream));
+    h->gather_used[idx] = true;
+    return 0;
+}
+
 static int infer_device_entry(smapb_handle* h, const float* imgs, const double* scales, int B, int do_flip, int gather,
                               smapb_record* records, void* stream) {
     if (!h) return -1;
@@ -1911,6 +1963,27 @@ int smapb_infer_device(smapb_handle* h, const float* imgs, const double* scales,
 int smapb_infer_device_gather(smapb_handle* h, const float* imgs, const double* scales, int B, int do_flip,
                               smapb_record* all_records, void* stream) {
     return infer_device_entry(h, imgs, scales, B, do_flip, 1, all_records, stream);
+}
+
+int smapb_infer_device_gather_async(smapb_handle* h, const float* imgs, const double* scales, int B, int do_flip,
+                                    smapb_record* all_records, void* stream) {
+    if (!h) return -1;
+    if (!h->finalized) return fail(h, -2, "smapb_infer_device_gather_async: weights not finalized");
+    cudaSetDevice(h->device);
+    if (stream) return infer_device_gather_async_impl(h, imgs, scales, B, do_flip, all_records, (cudaStream_t)stream);
+    int rc = legacy_enter(h);
+    if (!rc) rc = infer_device_gather_async_impl(h, imgs, scales, B, do_flip, all_records, h->own_stream);
+    if (!rc) rc = legacy_leave(h);
+    return rc;
+}
+
+int smapb_gather_sync(smapb_handle* h, void* stream) {
+    if (!h) return -1;
+    cudaSetDevice(h->device);
+    cudaStream_t st = stream ? (cudaStream_t)stream : cudaStreamLegacy;
+    for (int i = 0; i < 2; i++)
+        if (h->gather_used[i]) CK(cudaStreamWaitEvent(st, h->gather_done[i], 0));
+    return 0;
 }
 
 int smapb_infer_host(smapb_handle* h, const float* imgs_host, const double* scales_host, int B, int do_flip,
@@ -1959,13 +2032,26 @@ static int submit_host_impl(smapb_handle* h, int slot, const float* imgs_host, c
     CK(cudaEventRecord(S.h2d, h->copy_stream));
     cudaStream_t st = h->own_stream;
     CK(cudaStreamWaitEvent(st, S.h2d, 0));
-    smapb_record* dst = gather ? S.records_all : S.records;
-    int rc = infer_device_impl(h, S.imgs, S.scales, B, do_flip, gather, dst, st);
+    int rc = infer_device_impl(h, S.imgs, S.scales, B, do_flip, 0, S.records, st);
     if (rc) return rc;
-    // gather: the records were exchanged on the device (NVLink) before this single D2H - nothing is re-uploaded
-    CK(cudaMemcpyAsync(records_host, dst, (size_t)B * (gather ? h->comm_world : 1) * sizeof(smapb_record),
-                       cudaMemcpyDeviceToHost, st));
-    CK(cudaEventRecord(S.done, st));
+    if (!gather) {
+        CK(cudaMemcpyAsync(records_host, S.records, (size_t)B * sizeof(smapb_record), cudaMemcpyDeviceToHost, st));
+        CK(cudaEventRecord(S.done, st));
+    } else {
+        // The exchange and the D2H of its result run on the gather stream: the compute stream goes straight on to the next
+        // slot's batch and never waits for a peer.  The records are exchanged on the device (NVLink) and leave in ONE D2H -
+        // nothing is re-uploaded.
+        rc = gather_side_init(h);
+        if (rc) return rc;
+        if (!S.rec_ready) CK(cudaEventCreateWithFlags(&S.rec_ready, cudaEventDisableTiming));
+        CK(cudaEventRecord(S.rec_ready, st));
+        CK(cudaStreamWaitEvent(h->gather_stream, S.rec_ready, 0));
+        rc = gather_records(h, h->comm, S.records, S.records_all, B, h->gather_stream);
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(records_host, S.records_all, (size_t)B * h->comm_world * sizeof(smapb_record), cudaMemcpyDeviceToHost,
+                           h->gather_stream));
+        CK(cudaEventRecord(S.done, h->gather_stream));
+    }
     S.used = true;
     return 0;
 }

@@ -239,11 +239,13 @@ class Engine:
         self._check(self.lib.smapb_set_refine(self._h, int(bool(enable))), "smapb_set_refine")
 
     # ---- whole path ---------------------------------------------------------------------------
-    def infer_device(self, imgs, scales, do_flip=False, out=None, gather=False):
+    def infer_device(self, imgs, scales, do_flip=False, out=None, gather=False, defer=False):
         """imgs cuda fp32 [B,3,H,W], scales cuda f64 [B,9] -> records uint8 cuda [B, RECORD_BYTES]; gather=True (after
         init_comm): [world*B, RECORD_BYTES], all ranks' records in rank order, exchanged by ONE ncclAllGather on the same
-        stream (inside the same CUDA graph).  With an engine-owned stream the call is asynchronous with respect to torch's
-        current stream: pass `out` (preallocated) and order the streams yourself."""
+        stream (inside the same CUDA graph).  defer=True (with gather): the exchange runs on the handle's gather stream and
+        `out` is valid after gather_sync() - the compute stream never waits for peers (smapb_infer_device_gather_async).
+        With an engine-owned stream the call is asynchronous with respect to torch's current stream: pass `out`
+        (preallocated) and order the streams yourself."""
         B = imgs.shape[0]
         n = B * (self.world if gather else 1)
         if out is None:
@@ -251,10 +253,15 @@ class Engine:
             if self.stream is not None:
                 out.record_stream(self.stream)
         assert out.shape[0] == n and out.is_contiguous()
-        fn = self.lib.smapb_infer_device_gather if gather else self.lib.smapb_infer_device
+        fn = (self.lib.smapb_infer_device_gather_async if defer else self.lib.smapb_infer_device_gather) if gather \
+            else self.lib.smapb_infer_device
         self._check(fn(self._h, _ptr(imgs.contiguous()), _ptr(scales.contiguous()), B, int(do_flip), _ptr(out), self._st()),
                     "smapb_infer_device")
         return out
+
+    def gather_sync(self):
+        """Order this engine's stream (or torch's current stream) after every outstanding deferred exchange."""
+        self._check(self.lib.smapb_gather_sync(self._h, self._st()), "smapb_gather_sync")
 
     # ---- multi-GPU ------------------------------------------------------------------------------
     def init_comm(self, group=None):

@@ -49,6 +49,14 @@ def main():
         gathered.append(out.cpu())
     for g in gathered[1:]:
         assert torch.equal(g, gathered[0]), "gathered records changed between eager run and graph replay"
+    # decoupled form: exchange on the gather stream, valid after gather_sync; several calls in flight (double-buffered records)
+    outs = [torch.zeros(total, RECORD_BYTES, dtype=torch.uint8, device=dev) for _ in range(5)]
+    for o in outs:
+        eng.infer_device(mine, scales, out=o, gather=True, defer=True)
+    eng.gather_sync()
+    st.synchronize()
+    for o in outs:
+        assert torch.equal(o.cpu(), gathered[0]), "deferred exchange differs from the stream-ordered one"
     # host variant: H2D -> path -> device all-gather -> ONE D2H of the gathered records
     host_out = torch.zeros(total, RECORD_BYTES, dtype=torch.uint8).pin_memory()
     eng.submit_host(0, frames[lo:hi].contiguous().pin_memory(), scales.cpu().pin_memory(), host_out, gather=True)
