@@ -182,11 +182,18 @@ class CpuOracle:
 
 def ref_gpu_path_note():
     """The reference's own single-GPU path (eager PyTorch/cuDNN backbone + unmodified dapalib per image + numpy lift) is
-    measured builder-side by tests/ref_gpu_fps.py on the same kind of box; bench.py only quotes the committed number."""
+    measured builder-side by tests/ref_gpu_compare.py on the same kind of box; bench.py only quotes the committed numbers."""
     p = os.path.join(ROOT, "profiles", "r02_reference_gpu_path.json")
-    if os.path.exists(p):
-        return json.load(open(p))
-    return None
+    if not os.path.exists(p):
+        return None
+    d = json.load(open(p))
+    bb, e2e = d.get("backbone_only", {}), d.get("whole_gpu_path", {})
+    return {"value": d.get("value"), "unit": "frames/s", "what": d.get("what"),
+            "config4_15_persons_frames_per_s": e2e.get("reference_config4_15_persons", {}).get("frames_per_s"),
+            "backbone_only_ms_per_batch8": {"cudnn_tf32": bb.get("eager_cudnn_tf32_True_benchmark_False", {}).get("ms_per_batch"),
+                                            "cudnn_fp32": bb.get("eager_cudnn_tf32_False_benchmark_False", {}).get("ms_per_batch"),
+                                            "smap_b200_bf16x3": bb.get("smap_b200_bf16x3", {}).get("ms_per_batch")},
+            "source": "profiles/r02_reference_gpu_path.json (tests/ref_gpu_compare.py, builder-side run on a B200)"}
 
 
 def run_reference(args):
@@ -363,12 +370,12 @@ def run_ours(args):
     ms_dev, wall_dev = timed(run_device, args.steps)
     per_rank_ms = timed.per_rank
     launches = sum(e.launch_count() for e in engines) - l0
-    sampler.stop_flag = True
-    sampler.join(timeout=2)
 
     run_host(max(DEPTH, args.warmup))  # slot buffers + graphs for the slot pointers, then the host warm-up
     torch.cuda.synchronize()
     ms_host, wall_host = timed(run_host, args.steps)
+    sampler.stop_flag = True  # the clock sampler covers both timed regions (device-resident and host-buffer steps)
+    sampler.join(timeout=2)
 
     # roofline leg: per-kernel CUDA events on the launching stream (one handle, eager, every launch bracketed) give each
     # kernel's SHARE of the serialised step; the headline mode (graph replay, NE handles overlapping) cannot be
