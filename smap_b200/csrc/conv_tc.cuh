@@ -480,7 +480,7 @@ __global__ void __launch_bounds__(384, 1) conv_tc_kernel(const __grid_constant__
         int acc = 0;
         uint32_t acc_phase = 0;
         int rcnt = 0;
-        long long w_tfull = 0, w_stage = 0;
+        long long w_tfull = 0, w_stage = 0, w_ring = 0;
         for (int tile = blockIdx.x / CG; tile < p.total_tiles; tile += gridDim.x / CG) {
             const int te = p.reverse ? p.total_tiles - 1 - tile : tile;
             const int nt = te % p.n_tiles, mt = (te / p.n_tiles) * CG + (int)cta_rank;
@@ -511,7 +511,7 @@ __global__ void __launch_bounds__(384, 1) conv_tc_kernel(const __grid_constant__
                 auto ring_fetch = [&](uint4(&hh)[4], uint4(&ll)[4]) {
                     const int m = rcnt++;  // this group's FIFO position (mirrors the producer's cnt[g])
                     const int rslot = g * Cfg::SPG + (m % Cfg::SPG);
-                    mbar_wait(&rfull_bar[rslot], (uint32_t)(m / Cfg::SPG) & 1u);
+                    w_ring += mbar_wait_timed(&rfull_bar[rslot], (uint32_t)(m / Cfg::SPG) & 1u, p.dbg != nullptr && leader);
                     const uint32_t rb = res_stage + rslot * Cfg::SLOT_BYTES;
 #pragma unroll
                     for (int j = 0; j < 4; j++) {
@@ -648,6 +648,7 @@ __global__ void __launch_bounds__(384, 1) conv_tc_kernel(const __grid_constant__
         if (p.dbg && leader) {
             atomicAdd((unsigned long long*)&p.dbg[3 + 2 * g], (unsigned long long)w_tfull);
             atomicAdd((unsigned long long*)&p.dbg[4 + 2 * g], (unsigned long long)w_stage);
+            atomicAdd((unsigned long long*)&p.dbg[9 + g], (unsigned long long)w_ring);
         }
     }
 

@@ -2404,9 +2404,9 @@ int smapb_conv_test(smapb_handle* h, const float* x, const float* w, const float
         const double n = d[8] > 0 ? (double)d[8] : 1.0;  // number of MMA issuers (CTAs or pairs)
         fprintf(stderr,
                 "[roles] bn%d cg%d units%d kb%d | mean cycles per issuer: total %.0f | producer wait-empty %.0f | mma "
-                "wait-full %.0f wait-tempty %.0f | epi g0 wait-tfull %.0f wait-stage %.0f | g1 wait-tfull %.0f wait-stage %.0f\n",
+                "wait-full %.0f wait-tempty %.0f | epi g0 wait-tfull %.0f wait-stage %.0f wait-ring %.0f | g1 wait-tfull %.0f wait-stage %.0f wait-ring %.0f\n",
                 bn, cg, cp.total_tiles, cp.kh * cp.kw * cp.kchunks + cp.kchunks2, d[7] / n, d[0] / n / cg, d[1] / n,
-                d[2] / n, d[3] / n / cg, d[4] / n / cg, d[5] / n / cg, d[6] / n / cg);
+                d[2] / n, d[3] / n / cg, d[4] / n / cg, d[9] / n / cg, d[5] / n / cg, d[6] / n / cg, d[10] / n / cg);
         cp.dbg = nullptr;
     }
     const int reps = ms_out ? 5 : 0;
