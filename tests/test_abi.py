@@ -72,3 +72,28 @@ def test_create_reports_error_without_device():
     rc = lib.smapb_create(ctypes.byref(h), 0, 1, 512, 832)
     assert rc != 0 and not h.value
     assert len(lib.smapb_last_error(None)) > 0
+
+
+def test_tile_table_roundtrip_is_process_wide():
+    """smapb_set_tile_table / smapb_get_tile_table (no GPU): comments and malformed lines are skipped, entries overwrite."""
+    from smap_b200 import _lib, engine
+
+    lib = _lib.load()
+    n = lib.smapb_set_tile_table(b"# comment\nGEOM_A k1\t128\t2\nbroken line\nGEOM_B\t64\t1\nGEOM_A k1\t256\t2\n")
+    assert n == 3
+    txt = engine.get_tile_table()
+    rows = dict(l.split("\t", 1) for l in txt.strip().split("\n"))
+    assert rows["GEOM_A k1"] == "256\t2" and rows["GEOM_B"] == "64\t1"
+
+
+def test_committed_tile_table_covers_the_bench_and_smoke_batches():
+    import os
+
+    from smap_b200 import engine
+
+    rows = [l for l in open(engine.TILE_TABLE_PATH).read().split("\n") if l and not l.startswith("#")]
+    assert len(rows) > 100
+    for l in rows:
+        key, bn, cg = l.split("\t")
+        assert int(bn) in (32, 64, 128, 256) and int(cg) in (1, 2)
+    assert any(" 8x128x208 " in l for l in rows) and any(" 1x128x208 " in l for l in rows)

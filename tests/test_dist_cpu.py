@@ -57,3 +57,34 @@ def test_allgather_records_world2_gloo(n_frames):
         p.join(timeout=60)
         assert p.exitcode == 0
     assert all(ok for _, ok in res), res
+
+
+def _tile_worker(rank, world, port, q):
+    import torch.distributed as dist
+
+    from smap_b200 import _lib, dist as sdist, engine
+
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    lib = _lib.load()
+    # rank 0 "autotuned" two geometries, rank 1 a different choice for one of them: after the sync everyone holds rank 0's
+    lib.smapb_set_tile_table(b"G1\t128\t2\nG2\t64\t1\n" if rank == 0 else b"G1\t256\t1\n")
+    sdist.sync_tile_table()
+    q.put((rank, engine.get_tile_table()))
+    dist.destroy_process_group()
+
+
+def test_sync_tile_table_broadcasts_rank0_choices():
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29400 + os.getpid() % 300
+    ps = [ctx.Process(target=_tile_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    got = dict(q.get(timeout=120) for _ in range(2))
+    for p in ps:
+        p.join(60)
+    for r in range(2):
+        rows = dict(l.split("\t", 1) for l in got[r].strip().split("\n"))
+        assert rows["G1"] == "128\t2" and rows["G2"] == "64\t1"

@@ -107,6 +107,34 @@ def test_engine_pool_matches_single_engine(eng):
     pool.close()
 
 
+def test_graph_cache_evicts_least_recently_used_and_explicit_stream_matches(eng):
+    """Whole-path graphs are keyed by the input pointers (cap 16, LRU): a caller that passes a fresh tensor every time keeps
+    working - and keeps getting graphs - beyond the cap.  A handle issuing on its own torch stream gives the same bytes."""
+    from smap_b200.engine import RECORD_BYTES, Engine, scale_row
+
+    sc = lift_numpy.default_scale(1920, 1080)
+    scales = torch.from_numpy(np.stack([scale_row(sc)] * 1)).cuda()
+    x0 = schema.make_input(1, 512, 832, seed=60).cuda()
+    ref = eng.infer_device(x0, scales).cpu()
+    keep = []
+    for i in range(20):  # 20 distinct (imgs, scales) pointer pairs, each used three times (eager, eager/capture, replay)
+        xi = x0.clone()
+        keep.append(xi)
+        for _ in range(3):
+            assert torch.equal(eng.infer_device(xi, scales).cpu(), ref)
+    assert torch.equal(eng.infer_device(keep[0], scales).cpu(), ref)  # evicted long ago: captured again
+    st = torch.cuda.Stream()
+    e2 = Engine(0, max_batch=1, in_h=512, in_w=832, stream=st)
+    e2.load_state_dict(schema.make_state_dict(0, "identity"))
+    out = torch.zeros(1, RECORD_BYTES, dtype=torch.uint8, device="cuda")
+    st.wait_stream(torch.cuda.current_stream())
+    for _ in range(4):
+        e2.infer_device(x0, scales, out=out)
+    st.synchronize()
+    assert torch.equal(out.cpu(), ref)
+    e2.close()
+
+
 def test_forward_is_bit_stable_under_concurrent_gpu_load(eng):
     """Regression: the epilogue ring of conv_tc_kernel is refilled by TMA (async proxy) after generic-proxy reads; without
     a proxy fence before the release, a refill overtook in-flight reads when another stream kept HBM busy and single

@@ -1,5 +1,6 @@
 #!/bin/bash
 # compute-sanitizer over the small-shape workload; logs -> gpurun_out/sanitizer_*.log
+# (initcheck cannot see TMA stores: the library zero-fills TMA-stored buffers once at allocation so that it stays clean)
 mkdir -p gpurun_out
 export SMAPB_NO_TILE_TABLE=1 SMAPB_NO_AUTOTUNE=1
 for tool in memcheck synccheck initcheck racecheck; do
