@@ -3,7 +3,9 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libsmap_b200.so")
+# SMAPB_LIB: load another build of the same library (A/B comparisons of kernel changes, tools/gpu_ab.sh); the default is
+# the in-tree build
+LIB_PATH = os.environ.get("SMAPB_LIB") or os.path.join(HERE, "lib", "libsmap_b200.so")
 
 NJ, NL, MAXP, NC2D, SCALE_LEN = 15, 14, 127, 43, 9
 PREC_BF16X3, PREC_BF16 = 3, 1

@@ -22,31 +22,6 @@ __constant__ float c_bone_length[NL] = {26.42178982f, 48.36980909f, 14.88291009f
                                         39.03553194f, 12.4644364f, 48.19076948f, 39.03553252f};
 
 // ---------------------------------------------------------------------------------------------
-// plane staging: warp 0 issues the bulk copies (one 16 KB chunk per lane per round, so up to 32 copies are in
-// flight per CTA) and is the ONLY warp that polls the mbarrier; everyone else parks on the CTA barrier.  (Round 1
-// had one thread issue 32 KB chunks while all 1024 threads spun on mbarrier.try_wait: the polling traffic slowed the
-// very shared-memory writes it was waiting for - 15 GB/s per SM.)
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void stage_planes(float* dst, const float* src, uint32_t bytes, uint64_t* bar) {
-    if (threadIdx.x == 0) {
-        mbar_init(bar, 1);
-        fence_mbar_init();
-    }
-    __syncthreads();
-    if (threadIdx.x < 32) {
-        if (threadIdx.x == 0) mbar_arrive_expect_tx(bar, bytes);
-        __syncwarp();
-        const uint32_t CH = 16384;
-        for (uint32_t off = threadIdx.x * CH; off < bytes; off += 32 * CH) {
-            const uint32_t n = bytes - off < CH ? bytes - off : CH;
-            bulk_g2s((char*)dst + off, (const char*)src + off, n, bar);
-        }
-        mbar_wait(bar, 0);
-    }
-    __syncthreads();
-}
-
-// ---------------------------------------------------------------------------------------------
 // NMS in two streaming passes (replaces nmsRegisterKernel + thrust::exclusive_scan + writeResultKernel,
 // extensions/gpu/nmsBase.cu:10-135), for any map size:
 //   nms_flag_kernel    : every warp tests 32 consecutive pixels of a plane per step (3x3 strict maximum above the
@@ -365,20 +340,44 @@ paf_kernel(const float* __restrict__ hms, int nchan, int h, int w, const float* 
     float* out = scores + ((size_t)img * NL + l) * MAXP * MAXP;
 
     pdl_wait();
-    const int nA = (int)pA[0], nB = (int)pB[0];
-    if (nA > 0 && nB > 0) {
-        const float* src = hms + ((size_t)img * nchan + NJ + 2 * l) * hw;
-        if (STAGED) stage_planes(planes, src, (uint32_t)hw * 8u, bar);
-        const float* mapX = STAGED ? planes : src;
-        for (int i = threadIdx.x; i < nA; i += PAF_THREADS) {
-            pk[2 * i] = pA[3 * (i + 1)];
-            pk[2 * i + 1] = pA[3 * (i + 1) + 1];
-        }
-        for (int i = threadIdx.x; i < nB; i += PAF_THREADS) {
-            pk[2 * (MAXP + 1) + 2 * i] = pB[3 * (i + 1)];
-            pk[2 * (MAXP + 1) + 2 * i + 1] = pB[3 * (i + 1) + 1];
+    const float* src = hms + ((size_t)img * nchan + NJ + 2 * l) * hw;
+    // STAGED: the bulk copies of both planes are issued FIRST, before the candidate counts are even known; the counts and the
+    // two peak lists (dependent global loads, ~1 us each) then arrive while the copy engine streams the 213 KB.  An item with
+    // an empty peak list has staged its planes for nothing - on a frame that contains people every limb has candidates -
+    // but the critical path of an item shrinks from  counts -> planes -> peak lists -> scores  to  planes -> scores
+    // (B = 64 crowded scenes, round 2: 56 us before; profiles/ holds the capture of this form).
+    if (STAGED) {
+        if (threadIdx.x == 0) {
+            mbar_init(bar, 1);
+            fence_mbar_init();
         }
         __syncthreads();
+        // warp 0 issues the copies (one 16 KB chunk per lane per round: up to 32 in flight per CTA) and is the ONLY warp
+        // that polls the mbarrier; everyone else parks on the CTA barrier.  (Round 1 had one thread issue 32 KB chunks while
+        // all 1024 threads spun on mbarrier.try_wait: the polling traffic slowed the very shared-memory writes it was
+        // waiting for - 15 GB/s per SM.)
+        if (threadIdx.x < 32) {
+            const uint32_t bytes = (uint32_t)hw * 8u;
+            if (threadIdx.x == 0) mbar_arrive_expect_tx(bar, bytes);
+            __syncwarp();
+            const uint32_t CH = 16384;
+            for (uint32_t off = threadIdx.x * CH; off < bytes; off += 32 * CH)
+                bulk_g2s((char*)planes + off, (const char*)src + off, bytes - off < CH ? bytes - off : CH, bar);
+        }
+    }
+    const int nA = (int)pA[0], nB = (int)pB[0];
+    for (int i = threadIdx.x; i < nA; i += PAF_THREADS) {
+        pk[2 * i] = pA[3 * (i + 1)];
+        pk[2 * i + 1] = pA[3 * (i + 1) + 1];
+    }
+    for (int i = threadIdx.x; i < nB; i += PAF_THREADS) {
+        pk[2 * (MAXP + 1) + 2 * i] = pB[3 * (i + 1)];
+        pk[2 * (MAXP + 1) + 2 * i + 1] = pB[3 * (i + 1) + 1];
+    }
+    if (STAGED && threadIdx.x < 32) mbar_wait(bar, 0);  // (also for an empty item: the copies must land before the CTA retires)
+    __syncthreads();
+    if (nA > 0 && nB > 0) {
+        const float* mapX = STAGED ? planes : src;
         const float near_thr = __fdiv_rn(__fsqrt_rn((float)(w * h)), 150.f);
         const int npairs = nA * nB;
         for (int p = threadIdx.x; p < npairs; p += PAF_THREADS) {

@@ -162,6 +162,50 @@ __device__ __forceinline__ uint4 ldg_v4(const void* p) {
 }
 
 
+
+// ---- epilogue arithmetic: packed fp32 (FADD2) and mixed bf16 -> fp32 (FHADD / FHFMA) instructions of sm_100 -------------
+// All of them are IEEE round-to-nearest single operations, i.e. bit-identical to the scalar fp32 sequences they replace
+// (bf16 -> fp32 widening is exact): the point is the instruction count of the epilogue, which is latency bound.
+// (a0, a1) += (b0, b1)
+__device__ __forceinline__ void fadd2(float& a0, float& a1, float b0, float b1) {
+    asm("{\n\t.reg .b64 ra, rb;\n\tmov.b64 ra, {%0, %1};\n\tmov.b64 rb, {%2, %3};\n\tadd.rn.f32x2 ra, ra, rb;\n\t"
+        "mov.b64 {%0, %1}, ra;\n\t}"
+        : "+f"(a0), "+f"(a1)
+        : "f"(b0), "f"(b1));
+}
+// fp32(low / high bf16 half of w) + c
+__device__ __forceinline__ float add_bf16lo(uint32_t w, float c) {
+    float d;
+    asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %1;\n\tadd.rn.f32.bf16 %0, l, %2;\n\t}" : "=f"(d) : "r"(w), "f"(c));
+    return d;
+}
+__device__ __forceinline__ float add_bf16hi(uint32_t w, float c) {
+    float d;
+    asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %1;\n\tadd.rn.f32.bf16 %0, h, %2;\n\t}" : "=f"(d) : "r"(w), "f"(c));
+    return d;
+}
+// c - fp32(low / high bf16 half of w), as one fma with the bf16 constant -1 (the product is exact)
+__device__ __forceinline__ float sub_bf16lo(float c, uint32_t w) {
+    float d;
+    asm("{\n\t.reg .b16 l, h, m;\n\tmov.b32 {l, h}, %1;\n\tmov.b16 m, 0xbf80;\n\tfma.rn.f32.bf16 %0, l, m, %2;\n\t}"
+        : "=f"(d)
+        : "r"(w), "f"(c));
+    return d;
+}
+__device__ __forceinline__ float sub_bf16hi(float c, uint32_t w) {
+    float d;
+    asm("{\n\t.reg .b16 l, h, m;\n\tmov.b32 {l, h}, %1;\n\tmov.b16 m, 0xbf80;\n\tfma.rn.f32.bf16 %0, h, m, %2;\n\t}"
+        : "=f"(d)
+        : "r"(w), "f"(c));
+    return d;
+}
+// bf16x2 pack with round-to-nearest-even: low half = a, high half = b
+__device__ __forceinline__ uint32_t cvt_bf16x2(float a, float b) {
+    uint32_t w;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w) : "f"(b), "f"(a));
+    return w;
+}
+
 // ---- 2-CTA (cta_group::2) helpers -----------------------------------------------------------------
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
@@ -224,7 +268,8 @@ __device__ __forceinline__ long long mbar_wait_timed(uint64_t* bar, uint32_t par
     return clock64() - t0;
 }
 
-template <int BLOCK_N, int NTERMS, bool RING, int CG = 1>
+// RING: 0 = no epilogue inputs, 1 = residual / skip tensors through the ring, 2 = fused bilinear residual (up_mode)
+template <int BLOCK_N, int NTERMS, int RING, int CG = 1>
 struct ConvCfg {
     static constexpr int TA = (NTERMS == 3) ? 2 : 1;  // operand planes held per stage
     static constexpr int A_BYTES = 128 * 128;         // 128 rows x 64 bf16
@@ -252,10 +297,11 @@ struct ConvCfg {
     static_assert(BLOCK_N % 32 == 0 && BLOCK_N >= 32 && BLOCK_N <= 256, "BLOCK_N");
 };
 
-template <int BLOCK_N, int NTERMS, bool RING, int CG = 1>
+template <int BLOCK_N, int NTERMS, int RING, int CG = 1>
 __global__ void __launch_bounds__(384, 1) conv_tc_kernel(const __grid_constant__ ConvParams p) {
     using Cfg = ConvCfg<BLOCK_N, NTERMS, RING, CG>;
     constexpr int STAGES = Cfg::STAGES;
+    constexpr bool UP = (RING == 2);  // the ring carries low-resolution patches the epilogue interpolates
     extern __shared__ unsigned char smem_raw[];
     // control block at the front, operand ring + epilogue staging 1024-aligned behind it
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw);
@@ -456,7 +502,7 @@ __global__ void __launch_bounds__(384, 1) conv_tc_kernel(const __grid_constant__
                         mbar_wait(&rempty_bar[slot], ((uint32_t)(m / Cfg::SPG) & 1u) ^ 1u);
                         int cx = tx << p.tw_log2, cy = ty * p.th;
                         uint32_t bytes = Cfg::SLOT_BYTES;
-                        if (p.up_mode && e == 0) {  // low-resolution patch under this tile
+                        if (UP && e == 0) {  // low-resolution patch under this tile
                             cx = up_src_index(cx, p.up_Wi, p.Wout);
                             cy = up_src_index(cy, p.up_Hi, p.Hout);
                             bytes = (uint32_t)(p.up_pw * p.up_ph * 64 * Cfg::TA);
@@ -495,11 +541,28 @@ __global__ void __launch_bounds__(384, 1) conv_tc_kernel(const __grid_constant__
             w_tfull += mbar_wait_timed(&tfull_bar[acc], acc_phase, p.dbg != nullptr && leader);
             tc_fence_after();
             const uint32_t taddr = tmem_base + (uint32_t)(acc * BLOCK_N) + ((uint32_t)(q * 32) << 16);
+            // this group's chunks of the tile: c_first, c_first + c_step, ...
+            const int c_first = p.one_group ? (g == 0 ? 0 : Cfg::CHUNKS) : g;
+            const int c_step = p.one_group ? 1 : 2;
+            // The TMEM buffer goes back to the MMA issuer as soon as this thread holds its last accumulators in registers
+            // (not after the tile's last store): the next-but-one tile's main loop starts up to a chunk time earlier.
+            auto release_acc = [&]() {
+                tc_fence_before();
+                if (CG == 1 || cta_rank == 0) mbar_arrive(&tempty_bar[acc]);
+                else mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[acc]), 0u));  // the pair leader's barrier
+            };
+            uint32_t acc_r[32];
+            if (c_first < Cfg::CHUNKS) tmem_ld32(taddr + (uint32_t)(c_first * 32), acc_r);
+            else release_acc();
 #pragma unroll 1
-            for (int c = (p.one_group ? (g == 0 ? 0 : Cfg::CHUNKS) : g); c < Cfg::CHUNKS; c += (p.one_group ? 1 : 2)) {
+            for (int c = c_first; c < Cfg::CHUNKS; c += c_step) {
                 const int c0 = c * 32;
-                uint32_t acc_r[32];
-                tmem_ld32(taddr + (uint32_t)c0, acc_r);
+                // bias of these 32 columns (every lane reads the same address: L1 broadcasts), requested before the waits
+                float4 bia[8];
+                if (!UP) {  // (the interpolating variant has no registers to spare for an early request)
+#pragma unroll
+                    for (int j = 0; j < 8; j++) bia[j] = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0) + j);
+                }
                 // epilogue inputs arrive through the residual ring in the order [residual][post1][post2]
                 auto ring_release = [&](int rslot) {
                     // The slot is refilled by TMA (async proxy) while these were generic-proxy reads: without a proxy
@@ -522,6 +585,7 @@ __global__ void __launch_bounds__(384, 1) conv_tc_kernel(const __grid_constant__
                     // nothing left to wait for) measured 1.5 % slower - the refill's head start matters more
                     ring_release(rslot);
                 };
+                // vv += hi + lo (the fp32 value the two planes carry), two elements per packed add
                 auto add_planes = [&](float(&vv)[32], const uint4(&hh)[4], const uint4(&ll)[4]) {
 #pragma unroll
                     for (int j = 0; j < 4; j++) {
@@ -529,15 +593,16 @@ __global__ void __launch_bounds__(384, 1) conv_tc_kernel(const __grid_constant__
                         const uint32_t l[4] = {ll[j].x, ll[j].y, ll[j].z, ll[j].w};
 #pragma unroll
                         for (int e = 0; e < 4; e++) {
-                            vv[8 * j + 2 * e] += bf16lo_to_f(h[e]) + bf16lo_to_f(l[e]);
-                            vv[8 * j + 2 * e + 1] += bf16hi_to_f(h[e]) + bf16hi_to_f(l[e]);
+                            const float r0 = add_bf16lo(l[e], bf16lo_to_f(h[e]));
+                            const float r1 = add_bf16hi(l[e], bf16hi_to_f(h[e]));
+                            fadd2(vv[8 * j + 2 * e], vv[8 * j + 2 * e + 1], r0, r1);
                         }
                     }
                 };
                 uint4 rh[4], rl[4];
                 float upv[32];
-                if (RING && p.has_res && !p.up_mode) ring_fetch(rh, rl);
-                if (RING && p.up_mode) {
+                if (RING == 1 && p.has_res) ring_fetch(rh, rl);
+                if (UP) {
                     // bilinear x2 of the low-resolution patch in the ring slot (weights as ATen computes them)
                     const int m = rcnt++;
                     const int rslot = g * Cfg::SPG + (m % Cfg::SPG);
@@ -562,8 +627,8 @@ __global__ void __launch_bounds__(384, 1) conv_tc_kernel(const __grid_constant__
                             const uint32_t h[4] = {hh.x, hh.y, hh.z, hh.w}, l[4] = {ll.x, ll.y, ll.z, ll.w};
 #pragma unroll
                             for (int e = 0; e < 4; e++) {
-                                q[k][2 * e] = bf16lo_to_f(h[e]) + bf16lo_to_f(l[e]);
-                                q[k][2 * e + 1] = bf16hi_to_f(h[e]) + bf16hi_to_f(l[e]);
+                                q[k][2 * e] = add_bf16lo(l[e], bf16lo_to_f(h[e]));
+                                q[k][2 * e + 1] = add_bf16hi(l[e], bf16hi_to_f(h[e]));
                             }
                         }
 #pragma unroll
@@ -574,25 +639,34 @@ __global__ void __launch_bounds__(384, 1) conv_tc_kernel(const __grid_constant__
                     mbar_arrive(&rempty_bar[rslot]);
                 }
                 tmem_ld_wait();
+                if (UP) {
+#pragma unroll
+                    for (int j = 0; j < 8; j++) bia[j] = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0) + j);
+                }
                 float v[32];
 #pragma unroll
                 for (int j = 0; j < 8; j++) {
-                    const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0) + j);
-                    v[4 * j + 0] = __uint_as_float(acc_r[4 * j + 0]) + b.x;
-                    v[4 * j + 1] = __uint_as_float(acc_r[4 * j + 1]) + b.y;
-                    v[4 * j + 2] = __uint_as_float(acc_r[4 * j + 2]) + b.z;
-                    v[4 * j + 3] = __uint_as_float(acc_r[4 * j + 3]) + b.w;
+                    v[4 * j + 0] = __uint_as_float(acc_r[4 * j + 0]);
+                    v[4 * j + 1] = __uint_as_float(acc_r[4 * j + 1]);
+                    v[4 * j + 2] = __uint_as_float(acc_r[4 * j + 2]);
+                    v[4 * j + 3] = __uint_as_float(acc_r[4 * j + 3]);
+                    fadd2(v[4 * j + 0], v[4 * j + 1], bia[j].x, bia[j].y);
+                    fadd2(v[4 * j + 2], v[4 * j + 3], bia[j].z, bia[j].w);
                 }
-                if (RING && p.has_res && !p.up_mode) add_planes(v, rh, rl);
-                if (RING && p.up_mode) {
+                // the accumulators of this chunk are in registers: request the next chunk's (they arrive while this one is
+                // converted and stored), or hand the TMEM buffer back after the tile's last chunk
+                if (c + c_step < Cfg::CHUNKS) tmem_ld32(taddr + (uint32_t)((c + c_step) * 32), acc_r);
+                else release_acc();
+                if (RING == 1 && p.has_res) add_planes(v, rh, rl);
+                if (UP) {
 #pragma unroll
-                    for (int j = 0; j < 32; j++) v[j] += upv[j];
+                    for (int j = 0; j < 32; j += 2) fadd2(v[j], v[j + 1], upv[j], upv[j + 1]);
                 }
                 if (p.relu) {
 #pragma unroll
                     for (int j = 0; j < 32; j++) v[j] = fmaxf(v[j], 0.f);
                 }
-                for (int e = 0; RING && e < p.n_post; e++) {  // (relu(..) + skip1) + skip2, left to right
+                for (int e = 0; RING == 1 && e < p.n_post; e++) {  // (relu(..) + skip1) + skip2, left to right
                     ring_fetch(rh, rl);
                     add_planes(v, rh, rl);
                 }
@@ -611,11 +685,9 @@ __global__ void __launch_bounds__(384, 1) conv_tc_kernel(const __grid_constant__
 #pragma unroll
                         for (int e = 0; e < 4; e++) {
                             const float a = v[8 * j + 2 * e], b = v[8 * j + 2 * e + 1];
-                            const __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);  // one cvt.rn.bf16x2.f32
-                            const uint32_t hw = *reinterpret_cast<const uint32_t*>(&h2);
-                            const __nv_bfloat162 l2 = __floats2bfloat162_rn(a - bf16lo_to_f(hw), b - bf16hi_to_f(hw));
+                            const uint32_t hw = cvt_bf16x2(a, b);  // hi = bf16(v), two per instruction
                             hw_[e] = hw;
-                            lw_[e] = *reinterpret_cast<const uint32_t*>(&l2);
+                            lw_[e] = cvt_bf16x2(sub_bf16lo(a, hw), sub_bf16hi(b, hw));  // lo = bf16(v - hi)
                         }
                         sts_v4(ob + sw64_off(row, j), make_uint4(hw_[0], hw_[1], hw_[2], hw_[3]));
                         if (NTERMS == 3)
@@ -636,9 +708,6 @@ __global__ void __launch_bounds__(384, 1) conv_tc_kernel(const __grid_constant__
                             make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                 }
             }
-            tc_fence_before();
-            if (CG == 1 || cta_rank == 0) mbar_arrive(&tempty_bar[acc]);
-            else mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[acc]), 0u));  // the pair leader's barrier
             if (++acc == 2) {
                 acc = 0;
                 acc_phase ^= 1u;

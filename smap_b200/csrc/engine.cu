@@ -371,7 +371,7 @@ int make_w_map(smapb_handle* h, CUtensorMap* m, const __nv_bfloat16* ptr, int Ci
 // ------------------------------------------------------------------------------------------------
 // conv launch
 // ------------------------------------------------------------------------------------------------
-template <int BN, int NT, bool RING, int CG>
+template <int BN, int NT, int RING, int CG>
 cudaError_t launch_conv_inst2(const ConvParams& cp, int sm_count, cudaStream_t st, bool pdl) {
     using Cfg = ConvCfg<BN, NT, RING, CG>;
     static bool configured = false;
@@ -408,8 +408,9 @@ cudaError_t launch_conv_inst2(const ConvParams& cp, int sm_count, cudaStream_t s
 }
 template <int BN, int NT, int CG>
 cudaError_t launch_conv_inst(const ConvParams& cp, int sm_count, cudaStream_t st, bool pdl) {
-    return (cp.has_res + cp.n_post) ? launch_conv_inst2<BN, NT, true, CG>(cp, sm_count, st, pdl)
-                                    : launch_conv_inst2<BN, NT, false, CG>(cp, sm_count, st, pdl);
+    if (cp.up_mode) return launch_conv_inst2<BN, NT, 2, CG>(cp, sm_count, st, pdl);  // fused bilinear residual
+    return (cp.has_res + cp.n_post) ? launch_conv_inst2<BN, NT, 1, CG>(cp, sm_count, st, pdl)
+                                    : launch_conv_inst2<BN, NT, 0, CG>(cp, sm_count, st, pdl);
 }
 cudaError_t launch_conv(const ConvParams& cp, int block_n, int nterms, int sm_count, cudaStream_t st, bool pdl,
                         int cg = 1) {
@@ -429,7 +430,7 @@ cudaError_t launch_conv(const ConvParams& cp, int block_n, int nterms, int sm_co
     switch (block_n) {
         case 256:  // bf16x3: 2 x 96 KB operand stages + output staging fill the smem, no room for an epilogue-input ring
             if (nterms == 1) return launch_conv_inst<256, 1, 1>(cp, sm_count, st, pdl);
-            return (cp.has_res + cp.n_post) ? cudaErrorInvalidValue : launch_conv_inst2<256, 3, false, 1>(cp, sm_count, st, pdl);
+            return (cp.has_res + cp.n_post) ? cudaErrorInvalidValue : launch_conv_inst2<256, 3, 0, 1>(cp, sm_count, st, pdl);
         SMAPB_CASE(128)
         SMAPB_CASE(64)
         SMAPB_CASE(32)
