@@ -336,42 +336,75 @@ cudaError_t launch_upadd_relu(const __nv_bfloat16* a, long long a_ps, const __nv
 // Head merge: out[n,c,y,x] = (r4 + up(r3)) + up(r2) (model/smap.py:418 with :221) and NHWC(fp32, padded C)
 // -> NCHW fp32.  r3 / r2 may be null (plain transpose for det_d / root_d).  CTA = 32 pixels of one row.
 // ---------------------------------------------------------------------------------------------
+// bilinear tap combination in the contraction pattern the scalar expression
+//   h0 * (w0 * b00 + w1 * b01) + h1 * (w0 * b10 + w1 * b11)
+// compiles to (first product rounded, second fused), pinned so that vector and scalar call sites agree bit for bit
+__device__ __forceinline__ float bilin4(float h0, float h1, float w0, float w1, float b00, float b01, float b10, float b11) {
+    const float s0 = __fmaf_rn(w1, b01, __fmul_rn(w0, b00));
+    const float s1 = __fmaf_rn(w1, b11, __fmul_rn(w0, b10));
+    return __fmaf_rn(h1, s1, __fmul_rn(h0, s0));
+}
+
+// One thread = 4 channels (one 16-byte load per tap) of one pixel; the x coefficients of the CTA's 32 pixels are computed
+// once.  Channel groups above Cout are never read.
 __global__ void __launch_bounds__(256)
 head_merge_kernel(const float* __restrict__ r4, const float* __restrict__ r3, const float* __restrict__ r2, int N, int H,
                   int W, int H3, int W3, int H2, int W2, int Cpad, int Cout, float* __restrict__ out) {
     __shared__ float tile[64][33];
+    __shared__ int s_xi[32][4];    // xa0, xa1, xb0, xb1
+    __shared__ float s_xw[32][4];  // wa0, wa1, wb0, wb1
     const int x0 = blockIdx.x * 32, y = blockIdx.y, n = blockIdx.z;
     pdl_wait();
     int y0a = 0, y1a = 0, y0b = 0, y1b = 0;
     float ha0 = 0, ha1 = 0, hb0 = 0, hb1 = 0;
     if (r3) bilin_coeff(y, H3, H, y0a, y1a, ha0, ha1);
     if (r2) bilin_coeff(y, H2, H, y0b, y1b, hb0, hb1);
-    for (int i = threadIdx.x; i < 32 * Cpad; i += 256) {
-        const int px = i / Cpad, c = i - px * Cpad;
+    if (threadIdx.x < 32) {
+        const int x = min(x0 + (int)threadIdx.x, W - 1);
+        int i0 = 0, i1 = 0;
+        float l0 = 0, l1 = 0;
+        if (r3) bilin_coeff(x, W3, W, i0, i1, l0, l1);
+        s_xi[threadIdx.x][0] = i0, s_xi[threadIdx.x][1] = i1, s_xw[threadIdx.x][0] = l0, s_xw[threadIdx.x][1] = l1;
+        i0 = i1 = 0, l0 = l1 = 0;
+        if (r2) bilin_coeff(x, W2, W, i0, i1, l0, l1);
+        s_xi[threadIdx.x][2] = i0, s_xi[threadIdx.x][3] = i1, s_xw[threadIdx.x][2] = l0, s_xw[threadIdx.x][3] = l1;
+    }
+    __syncthreads();
+    const int G = (Cout + 3) / 4;  // channel groups that reach the output
+    for (int i = threadIdx.x; i < 32 * G; i += 256) {
+        const int px = i / G, c = (i - px * G) * 4;
         const int x = x0 + px;
-        float v = 0.f;
-        if (x < W && c < Cout) {
-            v = r4[(((size_t)n * H + y) * W + x) * Cpad + c];
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (x < W) {
+            v = __ldg(reinterpret_cast<const float4*>(r4 + (((size_t)n * H + y) * W + x) * Cpad + c));
             if (r3) {
-                int xa0, xa1;
-                float wa0, wa1;
-                bilin_coeff(x, W3, W, xa0, xa1, wa0, wa1);
+                const int xa0 = s_xi[px][0], xa1 = s_xi[px][1];
+                const float wa0 = s_xw[px][0], wa1 = s_xw[px][1];
                 const float* b = r3 + (size_t)n * H3 * W3 * Cpad + c;
-                const float up = ha0 * (wa0 * b[((size_t)y0a * W3 + xa0) * Cpad] + wa1 * b[((size_t)y0a * W3 + xa1) * Cpad]) +
-                                 ha1 * (wa0 * b[((size_t)y1a * W3 + xa0) * Cpad] + wa1 * b[((size_t)y1a * W3 + xa1) * Cpad]);
-                v = v + up;
+                const float4 b00 = __ldg(reinterpret_cast<const float4*>(b + ((size_t)y0a * W3 + xa0) * Cpad));
+                const float4 b01 = __ldg(reinterpret_cast<const float4*>(b + ((size_t)y0a * W3 + xa1) * Cpad));
+                const float4 b10 = __ldg(reinterpret_cast<const float4*>(b + ((size_t)y1a * W3 + xa0) * Cpad));
+                const float4 b11 = __ldg(reinterpret_cast<const float4*>(b + ((size_t)y1a * W3 + xa1) * Cpad));
+                v.x = __fadd_rn(v.x, bilin4(ha0, ha1, wa0, wa1, b00.x, b01.x, b10.x, b11.x));
+                v.y = __fadd_rn(v.y, bilin4(ha0, ha1, wa0, wa1, b00.y, b01.y, b10.y, b11.y));
+                v.z = __fadd_rn(v.z, bilin4(ha0, ha1, wa0, wa1, b00.z, b01.z, b10.z, b11.z));
+                v.w = __fadd_rn(v.w, bilin4(ha0, ha1, wa0, wa1, b00.w, b01.w, b10.w, b11.w));
             }
             if (r2) {
-                int xb0, xb1;
-                float wb0, wb1;
-                bilin_coeff(x, W2, W, xb0, xb1, wb0, wb1);
+                const int xb0 = s_xi[px][2], xb1 = s_xi[px][3];
+                const float wb0 = s_xw[px][2], wb1 = s_xw[px][3];
                 const float* b = r2 + (size_t)n * H2 * W2 * Cpad + c;
-                const float up = hb0 * (wb0 * b[((size_t)y0b * W2 + xb0) * Cpad] + wb1 * b[((size_t)y0b * W2 + xb1) * Cpad]) +
-                                 hb1 * (wb0 * b[((size_t)y1b * W2 + xb0) * Cpad] + wb1 * b[((size_t)y1b * W2 + xb1) * Cpad]);
-                v = v + up;
+                const float4 b00 = __ldg(reinterpret_cast<const float4*>(b + ((size_t)y0b * W2 + xb0) * Cpad));
+                const float4 b01 = __ldg(reinterpret_cast<const float4*>(b + ((size_t)y0b * W2 + xb1) * Cpad));
+                const float4 b10 = __ldg(reinterpret_cast<const float4*>(b + ((size_t)y1b * W2 + xb0) * Cpad));
+                const float4 b11 = __ldg(reinterpret_cast<const float4*>(b + ((size_t)y1b * W2 + xb1) * Cpad));
+                v.x = __fadd_rn(v.x, bilin4(hb0, hb1, wb0, wb1, b00.x, b01.x, b10.x, b11.x));
+                v.y = __fadd_rn(v.y, bilin4(hb0, hb1, wb0, wb1, b00.y, b01.y, b10.y, b11.y));
+                v.z = __fadd_rn(v.z, bilin4(hb0, hb1, wb0, wb1, b00.z, b01.z, b10.z, b11.z));
+                v.w = __fadd_rn(v.w, bilin4(hb0, hb1, wb0, wb1, b00.w, b01.w, b10.w, b11.w));
             }
         }
-        if (c < 64) tile[c][px] = v;
+        tile[c][px] = v.x, tile[c + 1][px] = v.y, tile[c + 2][px] = v.z, tile[c + 3][px] = v.w;
     }
     __syncthreads();
     for (int i = threadIdx.x; i < Cout * 32; i += 256) {

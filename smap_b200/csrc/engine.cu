@@ -225,7 +225,12 @@ struct smapb_handle {
     std::vector<std::string> prof_desc;  // description of that op
     std::vector<double> prof_flops;
     size_t prof_used = 0;
+    // per-launch role counters of the conv kernels inside a profiled (eager) run: SMAPB_ROLES_PLAN=<csv path>
+    long long* roles_dev = nullptr;  // [ROLES_CAP][16]
+    size_t roles_used = 0;
+    std::vector<std::string> roles_desc;
 };
+constexpr size_t ROLES_CAP = 4096;
 
 namespace {
 
@@ -1134,13 +1139,20 @@ int run_plan(smapb_handle* h, Plan* plan, const float* imgs, float* hm2d, float*
                 prof_mark(h, PK_STEM, st, "maxpool");
                 break;
             case OP_CONV:
-                CK(launch_conv(op.cp, op.block_n, h->nterms, h->sm_count - h->sm_reserve, st, h->use_pdl, op.cg));
+                if (h->profiling && h->roles_dev && h->roles_used < ROLES_CAP) {
+                    ConvParams cp = op.cp;  // same launch with the wait-cycle counters of every warp role switched on
+                    cp.dbg = h->roles_dev + 16 * h->roles_used++;
+                    CK(launch_conv(cp, op.block_n, h->nterms, h->sm_count - h->sm_reserve, st, h->use_pdl, op.cg));
+                } else {
+                    CK(launch_conv(op.cp, op.block_n, h->nterms, h->sm_count - h->sm_reserve, st, h->use_pdl, op.cg));
+                }
                 if (h->profiling) {
                     char d[160];
                     snprintf(d, sizeof d, "conv k%dx%d s%d cin%d cout%d out%dx%d bn%d cg%d tiles%d", op.cp.kh, op.cp.kw,
                              op.cp.stride, op.cp.kchunks * 64, op.cp.Cout, op.cp.Hout, op.cp.Wout, op.block_n, op.cg,
                              op.cp.total_tiles);
                     prof_mark(h, PK_CONV, st, d, op.flops);
+                    if (h->roles_dev) h->roles_desc.push_back(op.name + "," + d);
                 }
                 break;
             case OP_UPADD:
@@ -1288,6 +1300,7 @@ void smapb_destroy(smapb_handle* h) {
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (h->refine_buf) cudaFree(h->refine_buf);
+    if (h->roles_dev) cudaFree(h->roles_dev);
     if (h->pre_stage) cudaFree(h->pre_stage);
     for (auto& e : h->pre_cache) cudaFree(e.second.buf);
     delete h;
@@ -2260,6 +2273,13 @@ int smapb_profile_begin(smapb_handle* h) {
     if (!h) return -1;
     h->profiling = true;
     h->prof_used = 0;
+    if (getenv("SMAPB_ROLES_PLAN")) {
+        cudaSetDevice(h->device);
+        if (!h->roles_dev) CK(cudaMalloc((void**)&h->roles_dev, ROLES_CAP * 16 * sizeof(long long)));
+        CK(cudaMemset(h->roles_dev, 0, ROLES_CAP * 16 * sizeof(long long)));
+        h->roles_used = 0;
+        h->roles_desc.clear();
+    }
     return 0;
 }
 
@@ -2287,6 +2307,26 @@ int smapb_profile_end(smapb_handle* h, double* ms_by_kind, int* launches_by_kind
     }
     if (f) fclose(f);
     h->prof_used = 0;
+    if (h->roles_dev && h->roles_used && getenv("SMAPB_ROLES_PLAN")) {
+        // mean wait cycles per role and CTA (or CTA pair) of every conv launch of the profiled window
+        std::vector<long long> d(h->roles_used * 16);
+        CK(cudaMemcpy(d.data(), h->roles_dev, d.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+        FILE* g = fopen(getenv("SMAPB_ROLES_PLAN"), "w");
+        if (g) {
+            fprintf(g, "idx,name,desc,issuers,total,producer_wait_empty,mma_wait_full,mma_wait_tempty,g0_wait_tfull,g0_wait_stage,"
+                       "g0_wait_ring,g1_wait_tfull,g1_wait_stage,g1_wait_ring\n");
+            for (size_t i = 0; i < h->roles_used && i < h->roles_desc.size(); i++) {
+                const long long* r = &d[i * 16];
+                const double n = r[8] > 0 ? (double)r[8] : 1.0;
+                const double cg = strstr(h->roles_desc[i].c_str(), " cg2 ") ? 2.0 : 1.0;
+                fprintf(g, "%zu,%s,%.0f,%.0f,%.0f,%.0f,%.0f,%.0f,%.0f,%.0f,%.0f,%.0f,%.0f\n", i, h->roles_desc[i].c_str(), n,
+                        r[7] / n, r[0] / n / cg, r[1] / n, r[2] / n, r[3] / n / cg, r[4] / n / cg, r[9] / n / cg, r[5] / n / cg,
+                        r[6] / n / cg, r[10] / n / cg);
+            }
+            fclose(g);
+        }
+        h->roles_used = 0;
+    }
     return 0;
 }
 
