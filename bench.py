@@ -66,7 +66,11 @@ def measured_peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock / throttle reasons during the timed region (B200_PROFILING.md recipe).  NVML in-process (a sample every
+    few ms, so that even a 0.2 s timed region gets tens of samples); `nvidia-smi` polling (~0.15 s per sample) only when
+    the NVML binding is missing."""
+
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, gpu_index):
         super().__init__(daemon=True)
@@ -74,8 +78,46 @@ class ClockSampler(threading.Thread):
         self.samples, self.reasons = [], set()
         self.max_mhz = None
         self.stop_flag = False
+        self.source = "nvml"
+        self.nvml = self.handle = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            # CUDA_VISIBLE_DEVICES may renumber the devices: address the GPU by the UUID torch reports
+            import torch
+
+            uuid = str(torch.cuda.get_device_properties(gpu_index).uuid)
+            try:
+                self.handle = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+            except Exception:
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            self.nvml = pynvml
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nvml = self.handle = None
+            self.source = "nvidia-smi"
+
+    def _nvml_sample(self):
+        n = self.nvml
+        self.samples.append(float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
+        try:
+            mask = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+        except Exception:
+            mask = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+        for bit, name in self.REASONS.items():
+            if mask & bit:
+                self.reasons.add(name)
 
     def run(self):
+        if self.nvml is not None:
+            while not self.stop_flag:
+                try:
+                    self._nvml_sample()
+                except Exception:
+                    pass
+                time.sleep(0.005)
+            return
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -95,7 +137,7 @@ class ClockSampler(threading.Thread):
     def result(self):
         s = sorted(self.samples)
         return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
-                "samples": len(s)}
+                "samples": len(s), "source": self.source}
 
 
 # ------------------------------------------------------------------------------------------------

@@ -60,6 +60,7 @@ struct alignas(64) ConvParams {
     // (align_corners=True) before the ReLU.  up_mode = 0: plain residual.
     int up_mode, up_Hi, up_Wi, up_pw, up_ph;
     long long* dbg;  // optional: per-role wait-cycle counters (tools/conv_micro.py --roles), null in production
+    long long* dbg_tl;  // optional: clock64 time line of CTA 0 (SMAPB_TIMELINE, smapb_conv_test only), null in production
 };
 
 // ---- tcgen05 / TMA PTX wrappers -----------------------------------------------------------------
@@ -317,6 +318,10 @@ __global__ void __launch_bounds__(384, 1) conv_tc_kernel(const __grid_constant__
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    const bool tl = p.dbg_tl != nullptr && blockIdx.x == 0;  // time line of CTA 0: [0] entry [1] set-up done [2] first operands
+                                                            // [3] main loop end [4] last tile's accumulators [5..12] chunk ends [13] epilogue
+                                                            // done [14] exit
+    if (tl && threadIdx.x == 0) p.dbg_tl[0] = clock64();
     const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;  // rank 0 = pair leader (issues the MMAs)
     const int n_extra = RING ? p.has_res + p.n_post : 0;  // epilogue input tensors streamed through the ring
     const bool tma_out = p.out != nullptr;
@@ -367,6 +372,7 @@ __global__ void __launch_bounds__(384, 1) conv_tc_kernel(const __grid_constant__
     const int tiles_per_img = p.tiles_x * p.tiles_y;
     const int tw = 1 << p.tw_log2;
 
+    if (tl && threadIdx.x == 0) p.dbg_tl[1] = clock64();
     pdl_wait();     // inputs of this layer are produced by the previous kernel in the stream
     pdl_trigger();  // let the next kernel's CTAs be scheduled onto SMs as they drain (they block in their own wait)
 
@@ -439,6 +445,7 @@ __global__ void __launch_bounds__(384, 1) conv_tc_kernel(const __grid_constant__
                 const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BLOCK_N);
                 for (int kb = 0; kb < num_kb; kb++) {
                     w_full += mbar_wait_timed(&full_bar[stage], phase, p.dbg != nullptr);
+                    if (tl && tile == 0 && kb == 0) p.dbg_tl[2] = clock64();
                     tc_fence_after();
                     const uint32_t sbase = ring + stage * Cfg::STAGE_BYTES;
                     const uint64_t a0 = umma_desc_sw128(sbase);
@@ -474,6 +481,7 @@ __global__ void __launch_bounds__(384, 1) conv_tc_kernel(const __grid_constant__
                     acc_phase ^= 1u;
                 }
             }
+            if (tl) p.dbg_tl[3] = clock64();
             if (p.dbg) {
                 atomicAdd((unsigned long long*)&p.dbg[1], (unsigned long long)w_full);
                 atomicAdd((unsigned long long*)&p.dbg[2], (unsigned long long)w_tempty);
@@ -539,6 +547,8 @@ __global__ void __launch_bounds__(384, 1) conv_tc_kernel(const __grid_constant__
             const int n0 = nt * BLOCK_N;
 
             w_tfull += mbar_wait_timed(&tfull_bar[acc], acc_phase, p.dbg != nullptr && leader);
+            const bool tl_last = tl && leader && g == 0 && tile + (int)gridDim.x / CG >= p.total_tiles;
+            if (tl_last) p.dbg_tl[4] = clock64();
             tc_fence_after();
             const uint32_t taddr = tmem_base + (uint32_t)(acc * BLOCK_N) + ((uint32_t)(q * 32) << 16);
             // this group's chunks of the tile: c_first, c_first + c_step, ...
@@ -707,6 +717,7 @@ __global__ void __launch_bounds__(384, 1) conv_tc_kernel(const __grid_constant__
                         *reinterpret_cast<float4*>(p.out_f32 + off + j * 4) =
                             make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                 }
+                if (tl_last && c / c_step < 8) p.dbg_tl[5 + c / c_step] = clock64();
             }
             if (++acc == 2) {
                 acc = 0;
@@ -714,6 +725,7 @@ __global__ void __launch_bounds__(384, 1) conv_tc_kernel(const __grid_constant__
             }
         }
         if (leader && tma_out) bulk_wait_all();  // stores must be complete before the CTA retires
+        if (tl && leader && g == 0) p.dbg_tl[13] = clock64();
         if (p.dbg && leader) {
             atomicAdd((unsigned long long*)&p.dbg[3 + 2 * g], (unsigned long long)w_tfull);
             atomicAdd((unsigned long long*)&p.dbg[4 + 2 * g], (unsigned long long)w_stage);
@@ -732,6 +744,7 @@ __global__ void __launch_bounds__(384, 1) conv_tc_kernel(const __grid_constant__
         else
             asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::TMEM_COLS)
                          : "memory");
+        if (tl && lane == 0) p.dbg_tl[14] = clock64();
     }
 }
 

@@ -338,11 +338,12 @@ cudaError_t launch_upadd_relu(const __nv_bfloat16* a, long long a_ps, const __nv
 // ---------------------------------------------------------------------------------------------
 // bilinear tap combination in the contraction pattern the scalar expression
 //   h0 * (w0 * b00 + w1 * b01) + h1 * (w0 * b10 + w1 * b11)
-// compiles to (first product rounded, second fused), pinned so that vector and scalar call sites agree bit for bit
+// compiled to in the scalar form of this kernel (PTX of the round-1/2 builds: the row sums fuse their SECOND product,
+// the column sum its FIRST), pinned so that the result does not depend on how the surrounding code is written
 __device__ __forceinline__ float bilin4(float h0, float h1, float w0, float w1, float b00, float b01, float b10, float b11) {
     const float s0 = __fmaf_rn(w1, b01, __fmul_rn(w0, b00));
     const float s1 = __fmaf_rn(w1, b11, __fmul_rn(w0, b10));
-    return __fmaf_rn(h1, s1, __fmul_rn(h0, s0));
+    return __fmaf_rn(h0, s0, __fmul_rn(h1, s1));
 }
 
 // One thread = 4 channels (one 16-byte load per tap) of one pixel; the x coefficients of the CTA's 32 pixels are computed

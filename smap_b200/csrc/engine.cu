@@ -2438,6 +2438,11 @@ int smapb_conv_test(smapb_handle* h, const float* x, const float* w, const float
         CKT(cudaMemset(dbg_dev, 0, 16 * sizeof(long long)));
         cp.dbg = dbg_dev;
     }
+    long long* tl_dev = nullptr;
+    if (getenv("SMAPB_TIMELINE")) {
+        CKT(cudaMalloc((void**)&tl_dev, 16 * sizeof(long long)));
+        tmp.push_back(tl_dev);
+    }
     CKT(launch_conv(cp, bn, h->nterms, h->sm_count, st, false, cg));  // warm-up + result
     if (dbg_dev) {
         long long d[16];
@@ -2449,6 +2454,19 @@ int smapb_conv_test(smapb_handle* h, const float* x, const float* w, const float
                 bn, cg, cp.total_tiles, cp.kh * cp.kw * cp.kchunks + cp.kchunks2, d[7] / n, d[0] / n / cg, d[1] / n,
                 d[2] / n, d[3] / n / cg, d[4] / n / cg, d[9] / n / cg, d[5] / n / cg, d[6] / n / cg, d[10] / n / cg);
         cp.dbg = nullptr;
+    }
+    if (tl_dev) {  // time line of CTA 0 of one warm launch (cycles since kernel entry)
+        CKT(cudaMemset(tl_dev, 0, 16 * sizeof(long long)));
+        cp.dbg_tl = tl_dev;
+        CKT(launch_conv(cp, bn, h->nterms, h->sm_count, st, false, cg));
+        cp.dbg_tl = nullptr;
+        long long t[16];
+        CKT(cudaMemcpy(t, tl_dev, sizeof t, cudaMemcpyDeviceToHost));
+        fprintf(stderr, "[timeline] bn%d cg%d units%d kb%d | set-up %lld | first operands %lld | main loop end %lld | last acc %lld | chunk ends",
+                bn, cg, cp.total_tiles, cp.kh * cp.kw * cp.kchunks + cp.kchunks2, t[1] - t[0], t[2] - t[0], t[3] - t[0], t[4] - t[0]);
+        for (int i = 5; i < 13; i++)
+            if (t[i]) fprintf(stderr, " %lld", t[i] - t[0]);
+        fprintf(stderr, " | epilogue done %lld | exit %lld\n", t[13] - t[0], t[14] - t[0]);
     }
     const int reps = ms_out ? 5 : 0;
     cudaEventRecord(e0, st);

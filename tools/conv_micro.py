@@ -17,7 +17,10 @@ SHAPES = {
     "l3_c1": (8, 32, 52, 1024, 256, 1, 1, True, False),
     "l4_c2": (8, 16, 26, 512, 512, 3, 1, True, False),
 }
-names = sys.argv[1:] or list(SHAPES)
+# CONV_MICRO_BATCH=n overrides the batch of every shape (fewer tiles -> fewer SMs busy: separates per-SM from chip-wide limits)
+names = [a for a in sys.argv[1:] if not a.startswith("-")] or list(SHAPES)
+if os.environ.get("CONV_MICRO_BATCH"):
+    SHAPES = {k: (int(os.environ["CONV_MICRO_BATCH"]),) + v[1:] for k, v in SHAPES.items()}
 eng = Engine(0, max_batch=1, in_h=64, in_w=96)
 for n in names:
     B, H, W, Cin, Cout, k, s, relu, res = SHAPES[n]
