@@ -16,6 +16,19 @@ def _newer(a, b):
     return os.path.getmtime(a) > os.path.getmtime(b)
 
 
+def build_variant(name, defines):
+    """A/B variant of the library (tools only): same sources with extra -D flags -> lib/libsmap_b200_<name>.so."""
+    os.makedirs(LIBDIR, exist_ok=True)
+    objs = []
+    for s in SOURCES:
+        obj = os.path.join(LIBDIR, "%s_%s.o" % (os.path.splitext(s)[0], name))
+        objs.append(obj)
+        subprocess.check_call(["nvcc"] + NVCC_FLAGS + ["-D" + d for d in defines] + ["-c", os.path.join(CSRC, s), "-o", obj])
+    lib = os.path.join(LIBDIR, "libsmap_b200_%s.so" % name)
+    subprocess.check_call(["nvcc", "-shared", "-o", lib] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"])
+    return lib
+
+
 def build(force=False, verbose=False):
     os.makedirs(LIBDIR, exist_ok=True)
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "smap_b200.h")]
@@ -39,4 +52,8 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build(force="-f" in sys.argv, verbose="-v" in sys.argv))
+    if "--variant" in sys.argv:  # python -m smap_b200.build --variant kymajor SMAPB_TAP_KY_MAJOR
+        i = sys.argv.index("--variant")
+        print(build_variant(sys.argv[i + 1], sys.argv[i + 2:]))
+    else:
+        print(build(force="-f" in sys.argv, verbose="-v" in sys.argv))

@@ -270,14 +270,23 @@ __device__ __forceinline__ long long mbar_wait_timed(uint64_t* bar, uint32_t par
 }
 
 // RING: 0 = no epilogue inputs, 1 = residual / skip tensors through the ring, 2 = fused bilinear residual (up_mode)
-template <int BLOCK_N, int NTERMS, int RING, int CG = 1>
+// HALO: 3x3 stride-1 layers with 64 input channels.  Instead of nine shifted 128-pixel A tiles per 64-channel block (nine TMA
+// loads of the same pixels: these layers are L2 -> SM bound at a third of the MMA rate), the tile is 8 x 16 pixels and the
+// operand "stages" are three column-shifted HALO strips of 8 x 18 pixels (one per kx): a tile row of 8 pixels is exactly one
+// 1024-byte SWIZZLE_128B atom, so the A operand of tap (ky, kx) is strip kx read from row ky on - a plain K-major descriptor
+// whose start address moves by ky * 1024 bytes.  Three loads of 36 KB replace nine of 32 KB, and the weights of all nine taps
+// (this CTA's rows) stay resident in shared memory for the whole kernel.  Taps are visited kx-major (as in every other
+// variant, so that results do not depend on the variant): strip kx is free for the next tile after its three taps.
+template <int BLOCK_N, int NTERMS, int RING, int CG = 1, bool HALO = false>
 struct ConvCfg {
     static constexpr int TA = (NTERMS == 3) ? 2 : 1;  // operand planes held per stage
-    static constexpr int A_BYTES = 128 * 128;         // 128 rows x 64 bf16
+    static constexpr int HALO_ROWS = 18 * 8;           // 8 x 18 pixels per strip
+    static constexpr int A_BYTES = HALO ? HALO_ROWS * 128 : 128 * 128;  // rows x 64 bf16
     // CG = 2: a pair of CTAs (cta_group::2) computes a 256 x BLOCK_N tile; each CTA stages its own 128 rows of A and
     // BLOCK_N/2 rows of B, and owns the 128 x BLOCK_N slice of the accumulator in its TMEM
     static constexpr int B_BYTES = (BLOCK_N / CG) * 128;
-    static constexpr int STAGE_BYTES = TA * (A_BYTES + B_BYTES);
+    static constexpr int STAGE_BYTES = HALO ? TA * A_BYTES : TA * (A_BYTES + B_BYTES);
+    static constexpr int B_RES_BYTES = HALO ? 9 * TA * B_BYTES : 0;  // resident weights (HALO)
     static constexpr int CHUNK_COLS = 32;              // epilogue granularity (one tcgen05.ld x32)
     static constexpr int CHUNKS = BLOCK_N / CHUNK_COLS;
     static constexpr int CHUNK_BYTES = 128 * 64;       // one plane of one chunk: 128 rows x 32 bf16
@@ -289,18 +298,19 @@ struct ConvCfg {
     static constexpr int SPG = RING ? RES_BUFS / 2 : 1;  // ring slots per epilogue group
     static constexpr int EPI_BYTES = (OUT_BUFS + RES_BUFS) * SLOT_BYTES;
     static constexpr int SMEM_LIMIT = 227 * 1024;
-    static constexpr int STAGES_RAW = (SMEM_LIMIT - 2048 - EPI_BYTES) / STAGE_BYTES;
-    static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 2048;  // 1 KB control + 1 KB alignment slack
+    static constexpr int STAGES_RAW = (SMEM_LIMIT - 2048 - EPI_BYTES - B_RES_BYTES) / STAGE_BYTES;
+    static constexpr int STAGES = HALO ? 3 : STAGES_RAW > 8 ? 8 : STAGES_RAW;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + B_RES_BYTES + EPI_BYTES + 2048;  // 1 KB control + 1 KB alignment slack
     static constexpr int TMEM_COLS = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64) ? 64 : (2 * BLOCK_N <= 128) ? 128
                                      : (2 * BLOCK_N <= 256) ? 256 : 512;
-    static_assert(STAGES >= 2, "need at least a double buffer");
+    static_assert(STAGES >= 2 && STAGES_RAW >= STAGES, "need at least a double buffer");
     static_assert(BLOCK_N % 32 == 0 && BLOCK_N >= 32 && BLOCK_N <= 256, "BLOCK_N");
+    static_assert(!HALO || (RING == 0 && NTERMS == 3), "the halo variant has no epilogue inputs");
 };
 
-template <int BLOCK_N, int NTERMS, int RING, int CG = 1>
+template <int BLOCK_N, int NTERMS, int RING, int CG = 1, bool HALO = false>
 __global__ void __launch_bounds__(384, 1) conv_tc_kernel(const __grid_constant__ ConvParams p) {
-    using Cfg = ConvCfg<BLOCK_N, NTERMS, RING, CG>;
+    using Cfg = ConvCfg<BLOCK_N, NTERMS, RING, CG, HALO>;
     constexpr int STAGES = Cfg::STAGES;
     constexpr bool UP = (RING == 2);  // the ring carries low-resolution patches the epilogue interpolates
     extern __shared__ unsigned char smem_raw[];
@@ -312,8 +322,10 @@ __global__ void __launch_bounds__(384, 1) conv_tc_kernel(const __grid_constant__
     uint64_t* rfull_bar = tempty_bar + 2;
     uint64_t* rempty_bar = rfull_bar + Cfg::RES_BUFS;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rempty_bar + Cfg::RES_BUFS);
+    uint64_t* bres_bar = reinterpret_cast<uint64_t*>(smem_raw + 512);  // HALO: the resident weights have landed
     const uint32_t ring = (smem_u32(smem_raw) + 1024u + 1023u) & ~1023u;
-    const uint32_t out_stage = ring + STAGES * Cfg::STAGE_BYTES;
+    const uint32_t bres = ring + STAGES * Cfg::STAGE_BYTES;  // HALO: [tap][plane][BLOCK_N / CG rows] weights
+    const uint32_t out_stage = bres + Cfg::B_RES_BYTES;
     const uint32_t res_stage = out_stage + Cfg::OUT_BUFS * Cfg::SLOT_BYTES;
 
     const int warp = threadIdx.x >> 5;
@@ -346,6 +358,7 @@ __global__ void __launch_bounds__(384, 1) conv_tc_kernel(const __grid_constant__
             mbar_init(&rfull_bar[s], 1);
             mbar_init(&rempty_bar[s], 128);
         }
+        if (HALO) mbar_init(bres_bar, 1);
         fence_mbar_init();
     }
     if (warp == 2) {
@@ -378,7 +391,43 @@ __global__ void __launch_bounds__(384, 1) conv_tc_kernel(const __grid_constant__
 
     if (warp == 0) {
         // ============================ operand TMA producer ====================
-        if (lane == 0) {
+        if (lane == 0 && HALO) {
+            // weights first: all nine taps of this CTA's rows, resident for the whole kernel (n_tiles == 1)
+            const uint32_t bbar = (CG == 2) ? mapa_u32(smem_u32(bres_bar), 0u) : 0u;
+            if (cta_rank == 0) mbar_arrive_expect_tx(bres_bar, Cfg::B_RES_BYTES * CG);
+            const int brow = (int)cta_rank * (BLOCK_N / CG);
+            for (int tap = 0; tap < 9; tap++) {
+#pragma unroll
+                for (int t = 0; t < Cfg::TA; t++) {
+                    const uint32_t db = bres + (uint32_t)((tap * Cfg::TA + t) * Cfg::B_BYTES);
+                    if (CG == 1) tma_load_4d(db, &p.tmB, bres_bar, 0, brow, tap, t);
+                    else tma_load_4d_cg2(db, &p.tmB, bbar, 0, brow, tap, t);
+                }
+            }
+            // then, per tile, the three column-shifted strips of (th + 2) x 8 pixels; strip kx is stage kx
+            uint32_t phase = 0;
+            long long w_empty = 0;
+            for (int tile = blockIdx.x / CG; tile < p.total_tiles; tile += gridDim.x / CG) {
+                const int te = p.reverse ? p.total_tiles - 1 - tile : tile;
+                const int mt = te * CG + (int)cta_rank;
+                const int img = mt / tiles_per_img, r = mt - img * tiles_per_img;
+                const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
+                const int x_in0 = (tx << p.tw_log2) - p.pad_x, y_in0 = ty * p.th - p.pad_y;
+                for (int kx = 0; kx < 3; kx++) {
+                    w_empty += mbar_wait_timed(&empty_bar[kx], phase ^ 1u, p.dbg != nullptr);
+                    if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[kx], Cfg::STAGE_BYTES * CG);
+                    const uint32_t fbar = (CG == 2) ? mapa_u32(smem_u32(&full_bar[kx]), 0u) : 0u;
+#pragma unroll
+                    for (int t = 0; t < Cfg::TA; t++) {
+                        const uint32_t da = ring + (uint32_t)(kx * Cfg::STAGE_BYTES + t * Cfg::A_BYTES);
+                        if (CG == 1) tma_load_5d(da, &p.tmA, &full_bar[kx], 0, x_in0 + kx, y_in0, img, t);
+                        else tma_load_5d_cg2(da, &p.tmA, fbar, 0, x_in0 + kx, y_in0, img, t);
+                    }
+                }
+                phase ^= 1u;
+            }
+            if (p.dbg) atomicAdd((unsigned long long*)&p.dbg[0], (unsigned long long)w_empty);
+        } else if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
             long long w_empty = 0;
@@ -399,9 +448,15 @@ __global__ void __launch_bounds__(384, 1) conv_tc_kernel(const __grid_constant__
                     int kcol, tapc, ax, ay;
                     const CUtensorMap* amap;
                     if (kb < num_kb1) {
-                        const int tap = kb / p.kchunks, kc = kb - tap * p.kchunks;
-                        const int ky = tap / p.kw, kx = tap - ky * p.kw;
-                        amap = &p.tmA, kcol = kc * 64, tapc = tap, ax = x_in0 + kx, ay = y_in0 + ky;
+                        // taps are visited kx-major (kx outer, ky inner) in EVERY variant: the accumulation order - hence
+                        // every result bit - is the same whichever variant computes a layer (see HALO above)
+                        const int ts = kb / p.kchunks, kc = kb - ts * p.kchunks;
+#ifdef SMAPB_TAP_KY_MAJOR  // the order of the builds before the halo variant existed: only for A/B digests (tools/ab_hash.py)
+                        const int ky = ts / p.kw, kx = ts - ky * p.kw;
+#else
+                        const int kx = ts / p.kh, ky = ts - kx * p.kh;
+#endif
+                        amap = &p.tmA, kcol = kc * 64, tapc = ky * p.kw + kx, ax = x_in0 + kx, ay = y_in0 + ky;
                     } else {  // K-concatenated second input (1x1, own stride): weight columns continue after Cin
                         const int kc2 = kb - num_kb1;
                         amap = &p.tmA2, kcol = kc2 * 64, tapc = 0;
@@ -439,11 +494,43 @@ __global__ void __launch_bounds__(384, 1) conv_tc_kernel(const __grid_constant__
             uint32_t acc_phase = 0;
             long long w_full = 0, w_tempty = 0;
             const long long t_begin = p.dbg ? clock64() : 0;
+            if (HALO) {
+                mbar_wait(bres_bar, 0);
+                tc_fence_after();
+            }
             for (int tile = blockIdx.x / CG; tile < p.total_tiles; tile += gridDim.x / CG) {
                 w_tempty += mbar_wait_timed(&tempty_bar[acc], acc_phase ^ 1u, p.dbg != nullptr);
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BLOCK_N);
-                for (int kb = 0; kb < num_kb; kb++) {
+                if (HALO) {
+                    constexpr uint64_t A_STEP = (uint64_t)(Cfg::A_BYTES >> 4), B_STEP = (uint64_t)(Cfg::B_BYTES >> 4);
+                    for (int kx = 0; kx < 3; kx++) {
+                        w_full += mbar_wait_timed(&full_bar[kx], phase, p.dbg != nullptr);
+                        if (tl && tile == 0 && kx == 0) p.dbg_tl[2] = clock64();
+                        tc_fence_after();
+                        for (int ky = 0; ky < 3; ky++) {
+                            // strip kx from tile row ky on: 128 consecutive 128-byte rows, 1024-aligned
+                            const uint64_t a0 = umma_desc_sw128(ring + (uint32_t)(kx * Cfg::STAGE_BYTES + ky * 1024));
+                            const uint64_t b0 = umma_desc_sw128(bres + (uint32_t)((ky * 3 + kx) * Cfg::TA * Cfg::B_BYTES));
+#pragma unroll
+                            for (int k = 0; k < 4; k++) {
+                                const uint64_t ka = a0 + (uint64_t)(k * 2), kbd = b0 + (uint64_t)(k * 2);
+                                if (CG == 1) {
+                                    tc_mma_bf16(tmem_d, ka, kbd, idesc, (kx | ky | k) != 0);
+                                    tc_mma_bf16(tmem_d, ka + A_STEP, kbd, idesc, 1u);
+                                    tc_mma_bf16(tmem_d, ka, kbd + B_STEP, idesc, 1u);
+                                } else {
+                                    tc_mma_bf16_cg2(tmem_d, ka, kbd, idesc, (kx | ky | k) != 0);
+                                    tc_mma_bf16_cg2(tmem_d, ka + A_STEP, kbd, idesc, 1u);
+                                    tc_mma_bf16_cg2(tmem_d, ka, kbd + B_STEP, idesc, 1u);
+                                }
+                            }
+                        }
+                        if (CG == 1) tc_commit(&empty_bar[kx]); else tc_commit_cg2(&empty_bar[kx]);  // strip kx is free
+                    }
+                    phase ^= 1u;
+                }
+                for (int kb = 0; !HALO && kb < num_kb; kb++) {
                     w_full += mbar_wait_timed(&full_bar[stage], phase, p.dbg != nullptr);
                     if (tl && tile == 0 && kb == 0) p.dbg_tl[2] = clock64();
                     tc_fence_after();

@@ -376,12 +376,12 @@ int make_w_map(smapb_handle* h, CUtensorMap* m, const __nv_bfloat16* ptr, int Ci
 // ------------------------------------------------------------------------------------------------
 // conv launch
 // ------------------------------------------------------------------------------------------------
-template <int BN, int NT, int RING, int CG>
+template <int BN, int NT, int RING, int CG, bool HALO = false>
 cudaError_t launch_conv_inst2(const ConvParams& cp, int sm_count, cudaStream_t st, bool pdl) {
-    using Cfg = ConvCfg<BN, NT, RING, CG>;
+    using Cfg = ConvCfg<BN, NT, RING, CG, HALO>;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, NT, RING, CG>,
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, NT, RING, CG, HALO>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
         if (e != cudaSuccess) return e;
         configured = true;
@@ -409,7 +409,7 @@ cudaError_t launch_conv_inst2(const ConvParams& cp, int sm_count, cudaStream_t s
     }
     cfg.attrs = attr;
     cfg.numAttrs = na;
-    return cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, NT, RING, CG>, cp);
+    return cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, NT, RING, CG, HALO>, cp);
 }
 template <int BN, int NT, int CG>
 cudaError_t launch_conv_inst(const ConvParams& cp, int sm_count, cudaStream_t st, bool pdl) {
@@ -419,6 +419,10 @@ cudaError_t launch_conv_inst(const ConvParams& cp, int sm_count, cudaStream_t st
 }
 cudaError_t launch_conv(const ConvParams& cp, int block_n, int nterms, int sm_count, cudaStream_t st, bool pdl,
                         int cg = 1) {
+    if (cg == 3) {  // CTA pairs over halo strips (3x3 stride 1, 64 -> 64 channels, bf16x3): see ConvCfg
+        if (nterms != 3 || block_n != 64 || cp.has_res + cp.n_post + cp.up_mode) return cudaErrorInvalidValue;
+        return launch_conv_inst2<64, 3, 0, 2, true>(cp, sm_count, st, pdl);
+    }
     if (cg == 2) {  // CTA pairs (cta_group::2): 256 x {256,128,64} tiles, bf16x3 only
         if (nterms != 3) return cudaErrorInvalidValue;
         switch (block_n) {
@@ -458,6 +462,24 @@ int setup_conv(smapb_handle* h, const ConvLayer& L, const Act& in, const Act* re
     if (in2 && (in2->C != L.Cin2 || L.k != 1 || L.stride != 1)) return fail(h, -30, "conv " + L.name + ": bad fused pair");
     if (up && (res || post1)) return fail(h, -30, "conv " + L.name + ": up-residual excludes other epilogue inputs");
     const bool flat = (L.k == 1 && L.stride == 1 && (!in2 || L.stride2 == 1) && !up);
+    // cg = 3: the halo-strip variant of the CTA-pair kernel (conv_tc.cuh, ConvCfg): 3x3, stride 1, 64 -> 64 channels, no
+    // epilogue inputs; tiles are 8 x 16 pixels (a tile row = one swizzle atom).  SMAPB_NO_HALO=1 keeps the generic kernel.
+    const bool halo_ok = L.k == 3 && L.stride == 1 && L.pad == 1 && L.Cin == 64 && L.Cout_pad == 64 && !L.stem_s2d && !in2 && !up &&
+                         !res && !post1 && !post2 && out && !outf && h->nterms == 3 && cg_out;
+    if (!force_bn && getenv("SMAPB_FORCE_TILE")) {  // debug: "bn,cg" for every layer where it is valid
+        int fb = 0, fc = 1;
+        if (sscanf(getenv("SMAPB_FORCE_TILE"), "%d,%d", &fb, &fc) >= 1 && fb > 0 && L.Cout_pad % fb == 0 &&
+            !(fc == 3 && !(halo_ok && fb == 64)) &&
+            !(fc == 2 && (outf || !cg_out || fb < 64)) && !(fc != 2 && fc != 3 && fb == 256 && (res || post1 || up)))
+            force_bn = fb, force_cg = fc;
+    }
+#ifdef SMAPB_TAP_KY_MAJOR  // A/B build with the pre-halo tap order: the halo variant (kx-major by construction) is left out
+    static const bool halo_on = false;
+#else
+    static const bool halo_on = getenv("SMAPB_NO_HALO") == nullptr;
+#endif
+    if (force_cg == 3 && !(halo_ok && force_bn == 64)) return fail(h, -31, "invalid forced tile");
+    const bool halo = halo_ok && (force_bn ? force_cg == 3 : halo_on);
     int tw, th, tiles_x, tiles_y, nimg;
     int rc;
     if (flat) {
@@ -476,7 +498,7 @@ int setup_conv(smapb_handle* h, const ConvLayer& L, const Act& in, const Act* re
         double best = -1;
         tw = 16;
         const int smax = in2 ? (L.stride2 > L.stride ? L.stride2 : L.stride) : L.stride;
-        for (int c = 128; c >= 1; c >>= 1) {
+        for (int c = halo ? 8 : 128; c >= (halo ? 8 : 1); c >>= 1) {
             const int t_h = 128 / c;
             if (c * smax > 256 || t_h * smax > 256) continue;
             if (up && (c / 2 + 2) * (t_h / 2 + 2) > 128) continue;  // the low-resolution patch must fit one ring slot
@@ -492,8 +514,11 @@ int setup_conv(smapb_handle* h, const ConvLayer& L, const Act& in, const Act* re
         nimg = N;
         cp->Hout = Ho;
         cp->Wout = Wo;
-        rc = make_act_map(h, &cp->tmA, in.ptr, in.C, in.W, in.H, N, h->planes, in.plane(), tw * L.stride,
-                          th * L.stride, L.stride);
+        if (halo)  // one column-shifted strip of (th + 2) x tw pixels per load
+            rc = make_act_map(h, &cp->tmA, in.ptr, in.C, in.W, in.H, N, h->planes, in.plane(), tw, th + 2, 1);
+        else
+            rc = make_act_map(h, &cp->tmA, in.ptr, in.C, in.W, in.H, N, h->planes, in.plane(), tw * L.stride,
+                              th * L.stride, L.stride);
         if (!rc && in2)
             rc = make_act_map(h, &cp->tmA2, in2->ptr, in2->C, in2->W, in2->H, N, h->planes, in2->plane(),
                               tw * L.stride2, th * L.stride2, L.stride2);
@@ -541,19 +566,15 @@ int setup_conv(smapb_handle* h, const ConvLayer& L, const Act& in, const Act* re
             if (t < best - 1e-9) best = t, bn = c, cg = pair ? 2 : 1;
         }
         if (!bn) return fail(h, -30, "conv " + L.name + ": no tile shape for Cout_pad " + std::to_string(L.Cout_pad));
-    }
-    if (!force_bn && getenv("SMAPB_FORCE_TILE")) {  // debug: "bn,cg" for every layer where it is valid
-        int fb = 0, fc = 1;
-        if (sscanf(getenv("SMAPB_FORCE_TILE"), "%d,%d", &fb, &fc) >= 1 && fb > 0 && L.Cout_pad % fb == 0 &&
-            !(fc == 2 && (outf || !cg_out || fb < 64)) && !(fc != 2 && fb == 256 && (res || post1 || up)))
-            force_bn = fb, force_cg = fc;
+        if (halo) bn = 64, cg = 3;
     }
     if (force_bn) {  // autotuner override
         bn = force_bn;
         cg = force_cg ? force_cg : 1;
         // one-CTA 128 x 256 tiles in bf16x3 have room for two 96 KB operand stages only without an epilogue-input ring
         const bool needs_ring = res || post1 || up;
-        if (L.Cout_pad % bn || (cg == 2 && ((bn != 256 && bn != 128 && bn != 64) || h->nterms != 3 || outf || !cg_out)) ||
+        if (L.Cout_pad % bn || (cg == 3 && !halo) ||
+            (cg == 2 && ((bn != 256 && bn != 128 && bn != 64) || h->nterms != 3 || outf || !cg_out)) ||
             (cg == 1 && bn == 256 && h->nterms == 3 && needs_ring))
             return fail(h, -31, "invalid forced tile");
     }
@@ -568,7 +589,8 @@ int setup_conv(smapb_handle* h, const ConvLayer& L, const Act& in, const Act* re
     cp->kchunks2 = L.Cin2 / 64;
     cp->stride2 = L.stride2;
     cp->n_tiles = L.Cout_pad / bn;
-    cp->total_tiles = (int)((cg == 2 ? (m_tiles + 1) / 2 : m_tiles) * cp->n_tiles);  // work units (tiles or pair tiles)
+    const int cs = cg >= 2 ? 2 : 1;  // CTAs per work unit (cluster size)
+    cp->total_tiles = (int)((cs == 2 ? (m_tiles + 1) / 2 : m_tiles) * cp->n_tiles);  // work units (tiles or pair tiles)
     cp->bias = L.bias_dev;
     cp->has_res = (res || up) ? 1 : 0;
     cp->n_post = (post1 ? 1 : 0) + (post2 ? 1 : 0);
@@ -599,7 +621,7 @@ int setup_conv(smapb_handle* h, const ConvLayer& L, const Act& in, const Act* re
                 cp->one_group = 1;
         }
     }
-    rc = make_w_map(h, &cp->tmB, L.w_dev, L.Cin + L.Cin2, L.Cout_pad, L.k * L.k, h->planes, bn / cg);
+    rc = make_w_map(h, &cp->tmB, L.w_dev, L.Cin + L.Cin2, L.Cout_pad, L.k * L.k, h->planes, bn / cs);
     if (rc) return rc;
     // epilogue tiles: 32 channels x (tw x th) pixels of the output / residual planes
     int n_in = up ? 1 : 0;
@@ -830,10 +852,10 @@ struct PlanBuilder {
             cudaEventCreate(&e0);
             cudaEventCreate(&e1);
             float best_ms = 1e30f;
-            const int cand[7][2] = {{128, 1}, {64, 1}, {256, 2}, {128, 2}, {64, 2}, {256, 1}, {32, 1}};
+            const int cand[8][2] = {{128, 1}, {64, 1}, {256, 2}, {128, 2}, {64, 2}, {256, 1}, {32, 1}, {64, 3}};
             for (auto& c : cand) {
                 if (L.Cout_pad % c[0]) continue;
-                if (c[1] == 2 && h->nterms != 3) continue;
+                if (c[1] >= 2 && h->nterms != 3) continue;
                 if (c[0] == 32 && L.Cout_pad > 64) continue;
                 if (c[0] == 256 && c[1] == 1 && getenv("SMAPB_NO_BN256")) continue;  // A/B switch for the 128 x 256 one-CTA tiles
                 Op trial;
@@ -2174,7 +2196,7 @@ int smapb_set_tile_table(const char* text) {
         if (t1 == std::string::npos) continue;
         int bn = 0, cg = 1;
         if (sscanf(line.c_str() + t1 + 1, "%d\t%d", &bn, &cg) < 1 || bn <= 0) continue;
-        g_tiles[line.substr(0, t1)] = {bn, cg == 2 ? 2 : 1};
+        g_tiles[line.substr(0, t1)] = {bn, (cg == 2 || cg == 3) ? cg : 1};
         n++;
     }
     return n;
@@ -2318,7 +2340,7 @@ int smapb_profile_end(smapb_handle* h, double* ms_by_kind, int* launches_by_kind
             for (size_t i = 0; i < h->roles_used && i < h->roles_desc.size(); i++) {
                 const long long* r = &d[i * 16];
                 const double n = r[8] > 0 ? (double)r[8] : 1.0;
-                const double cg = strstr(h->roles_desc[i].c_str(), " cg2 ") ? 2.0 : 1.0;
+                const double cg = (strstr(h->roles_desc[i].c_str(), " cg2 ") || strstr(h->roles_desc[i].c_str(), " cg3 ")) ? 2.0 : 1.0;
                 fprintf(g, "%zu,%s,%.0f,%.0f,%.0f,%.0f,%.0f,%.0f,%.0f,%.0f,%.0f,%.0f,%.0f\n", i, h->roles_desc[i].c_str(), n,
                         r[7] / n, r[0] / n / cg, r[1] / n, r[2] / n, r[3] / n / cg, r[4] / n / cg, r[9] / n / cg, r[5] / n / cg,
                         r[6] / n / cg, r[10] / n / cg);
@@ -2448,11 +2470,12 @@ int smapb_conv_test(smapb_handle* h, const float* x, const float* w, const float
         long long d[16];
         CKT(cudaMemcpy(d, dbg_dev, sizeof d, cudaMemcpyDeviceToHost));
         const double n = d[8] > 0 ? (double)d[8] : 1.0;  // number of MMA issuers (CTAs or pairs)
+        const double cs = cg >= 2 ? 2.0 : 1.0;
         fprintf(stderr,
                 "[roles] bn%d cg%d units%d kb%d | mean cycles per issuer: total %.0f | producer wait-empty %.0f | mma "
                 "wait-full %.0f wait-tempty %.0f | epi g0 wait-tfull %.0f wait-stage %.0f wait-ring %.0f | g1 wait-tfull %.0f wait-stage %.0f wait-ring %.0f\n",
-                bn, cg, cp.total_tiles, cp.kh * cp.kw * cp.kchunks + cp.kchunks2, d[7] / n, d[0] / n / cg, d[1] / n,
-                d[2] / n, d[3] / n / cg, d[4] / n / cg, d[9] / n / cg, d[5] / n / cg, d[6] / n / cg, d[10] / n / cg);
+                bn, cg, cp.total_tiles, cp.kh * cp.kw * cp.kchunks + cp.kchunks2, d[7] / n, d[0] / n / cs, d[1] / n,
+                d[2] / n, d[3] / n / cs, d[4] / n / cs, d[9] / n / cs, d[5] / n / cs, d[6] / n / cs, d[10] / n / cs);
         cp.dbg = nullptr;
     }
     if (tl_dev) {  // time line of CTA 0 of one warm launch (cycles since kernel entry)

@@ -122,3 +122,28 @@ def test_every_tile_shape_gives_the_same_bits(eng, monkeypatch, case):
         assert torch.equal(y, first), "tile %s differs from tile %s in %d elements" % (tile, _TILES[0], (y != first).sum().item())
         n += 1
     assert n >= 2
+
+
+@pytest.mark.parametrize("B,H,W", [(2, 128, 208), (1, 40, 40), (3, 37, 45)])
+def test_halo_strip_variant_matches_generic_tiles(eng, monkeypatch, B, H, W):
+    """3x3 stride-1 64 -> 64 layers run on the halo-strip variant of the pair kernel (tile = 8 x 16 pixels, three
+    column-shifted strips instead of nine shifted tiles, weights resident; conv_tc.cuh ConvCfg): same bits as the generic
+    tiles, also with ragged borders and an odd number of tiles (the second CTA of the last pair has no tile)."""
+    g = torch.Generator(device="cpu").manual_seed(13)
+    x = torch.randn(B, H, W, 64, generator=g).cuda()
+    w = (torch.randn(64, 64, 3, 3, generator=g) / (64 * 9) ** 0.5).cuda()
+    b = torch.randn(64, generator=g).cuda()
+    ref = F.relu(F.conv2d(x.permute(0, 3, 1, 2), w, b, padding=1).permute(0, 2, 3, 1))
+    outs = {}
+    for tile in ("64,3", "64,2", "64,1"):
+        monkeypatch.setenv("SMAPB_FORCE_TILE", tile)
+        y = eng.conv_test(x, w, b, relu=True)
+        torch.cuda.synchronize()
+        err = (y - ref).abs().max().item() / ref.abs().max().item()
+        assert err < 2e-5, "tile %s: relative error %g" % (tile, err)
+        outs[tile] = y
+    monkeypatch.delenv("SMAPB_FORCE_TILE")
+    assert torch.equal(outs["64,3"], outs["64,2"]), "%d elements differ" % (outs["64,3"] != outs["64,2"]).sum().item()
+    assert torch.equal(outs["64,2"], outs["64,1"])
+    y = eng.conv_test(x, w, b, relu=True)  # the default choice for this geometry is the halo variant
+    assert torch.equal(y, outs["64,3"])
