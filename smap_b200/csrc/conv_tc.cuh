@@ -823,6 +823,7 @@ __global__ void __launch_bounds__(384, 1) conv_tc_kernel(const __grid_constant__
     tc_fence_before();
     __syncthreads();
     if (CG == 2) cluster_sync_all();  // the leader's MMAs read this CTA's smem: nobody leaves before both are done
+    if (tl && threadIdx.x == 64) p.dbg_tl[15] = clock64();
     if (warp == 2) {
         tc_fence_after();
         if (CG == 1)

@@ -2489,7 +2489,8 @@ int smapb_conv_test(smapb_handle* h, const float* x, const float* w, const float
                 bn, cg, cp.total_tiles, cp.kh * cp.kw * cp.kchunks + cp.kchunks2, t[1] - t[0], t[2] - t[0], t[3] - t[0], t[4] - t[0]);
         for (int i = 5; i < 13; i++)
             if (t[i]) fprintf(stderr, " %lld", t[i] - t[0]);
-        fprintf(stderr, " | epilogue done %lld | exit %lld\n", t[13] - t[0], t[14] - t[0]);
+        fprintf(stderr, " | epilogue done %lld | all warps + pair sync %lld | TMEM released, exit %lld\n", t[13] - t[0], t[15] - t[0],
+                t[14] - t[0]);
     }
     const int reps = ms_out ? 5 : 0;
     cudaEventRecord(e0, st);
