@@ -216,7 +216,9 @@ int64_t smapb_launch_count(const smapb_handle* h);
  * 6-element arrays and, if csv_path is not NULL, writes one line per launch. */
 int smapb_profile_begin(smapb_handle* h);
 int smapb_profile_end(smapb_handle* h, double* ms_by_kind, int* launches_by_kind, const char* csv_path);
-/* Tile shapes of the tensor-core convolutions (process-wide): one line per layer geometry, "key<TAB>BLOCK_N<TAB>cta_group".
+/* Tile shapes of the tensor-core convolutions (process-wide): one line per layer geometry, "key<TAB>BLOCK_N<TAB>cta_group"
+ * (cta_group: 1 = one CTA per 128-row tile, 2 = CTA pair (cta_group::2) per 256-row tile, 3 = CTA pair over halo strips - the
+ * 3x3 stride-1 64->64 variant).  Whatever shape computes a layer, the result bits are the same.
  * Geometries found in the table use its entry; others are autotuned once per process (SMAPB_NO_AUTOTUNE=1: cost model)
  * and added to it.  Loading the same table in every process makes tile selection - and with it every result bit -
  * independent of the handle, the process and the rank.  smapb_get_tile_table returns the bytes needed (incl. the

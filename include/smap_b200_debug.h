@@ -28,7 +28,7 @@ int smapb_debug_resize_plan(int src_w, int src_h, int net_w, int net_h, int* dim
  *   SMAPB_DEBUG_SYNC=1        synchronise the stream after every launch
  *   SMAPB_DEBUG_ONEGROUP=fpro one epilogue group for fp32-out / post-add / residual / other layers
  *   SMAPB_FORCE_TILE=bn,cg    force a tile shape wherever it is valid;  SMAPB_NO_AUTOTUNE=1  cost model only
- *   SMAPB_PAIR=0|1|2          CTA pairs off / model / always;  SMAPB_NO_BN256=1  no one-CTA 128x256 tiles
+ *   SMAPB_PAIR=0|1|2          CTA pairs off / model / always;  SMAPB_NO_BN256=1  no one-CTA 128x256 tiles;  SMAPB_NO_HALO=1  no halo strips
  *   SMAPB_ONE_STREAM=1        no side stream;  SMAPB_NO_GRAPH=1  no CUDA graph replay;  SMAPB_PDL=1  programmatic dependent launch
  *   SMAPB_STEM=cuda           CUDA-core stem;  SMAPB_NO_FUSE_DS=1 / SMAPB_NO_FUSE_UP=1  unfused downsample / up-residual
  *   SMAPB_ROLES=1             per-role wait-cycle counters in smapb_conv_test
