@@ -1,5 +1,6 @@
 #!/bin/bash
-# multi-GPU pass (gpurun --gpus N): sharding-invariance test under torchrun, then bench at 1 and N GPUs on the same box
+# multi-GPU pass (gpurun --gpus N -- 'bash tools/gpu_multi.sh N'): sharding-invariance test under torchrun, then bench at 1 and N GPUs
+# on the same box (every GPU of the box is charged: N = 2 is enough to exercise the gathered path)
 N=${1:-2}
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests/test_multigpu_gpu.py -q -m gpu -x -s > gpurun_out/pytest_multigpu_n$N.log 2>&1; echo "pytest multigpu rc=$?" > gpurun_out/summary_multi.txt
