@@ -21,7 +21,12 @@
 // Pipelines: operand full/empty ring (TMA <-> MMA), double-buffered TMEM accumulators (MMA <-> epilogue),
 // residual full/empty ring (TMA <-> epilogue), bulk-async store groups (epilogue <-> TMA store).
 // The epilogue never touches global memory with per-thread loads/stores on the main path: the residual tile
-// arrives by TMA ahead of time and the output leaves by TMA in 32-channel x 128-pixel boxes.
+// arrives by TMA ahead of time and the output leaves by TMA in 32-channel x 128-pixel boxes.  It is latency bound (one
+// dependent chain per 32-column chunk, two warps per scheduler), so it is written for few instructions - packed fp32
+// adds and mixed bf16/fp32 adds and fmas of sm_100 - and for overlap: the next chunk's accumulators are requested from
+// TMEM while the current chunk is converted, and the accumulator buffer is handed back after the tile's last read.
+// Taps of a k x k filter are visited kx-major; all variants (tile widths, CTA pairs, halo strips) accumulate every output
+// element in the same order, i.e. produce the same bits.
 #pragma once
 #include <cuda.h>
 #include "common.cuh"

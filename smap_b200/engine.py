@@ -31,7 +31,7 @@ def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
-TILE_TABLE_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "tiles", "b200.tsv")
+TILE_TABLE_PATH = os.environ.get("SMAPB_TILE_TABLE") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "tiles", "b200.tsv")  # SMAPB_TILE_TABLE: another table (A/B of a re-tune)
 _tile_table_loaded = False
 
 

@@ -4,6 +4,7 @@
 #   timeline  clock64 time line of CTA 0 (set-up, first operands, chunk ends, exit)  -> profiles/r02_conv_timeline_*.txt
 #   halo      halo-strip variant against the generic pair tile on the 3x3 64->64 layer -> profiles/r02_halo_variant_ab.txt
 #   toggles   bench with PDL / three handles against the default, back to back
+#   retune    re-measured tile table for batch 8 against the committed one (bench under both, alternating)
 mkdir -p gpurun_out
 case "$1" in
   roles)
@@ -25,5 +26,17 @@ for f in sorted(glob.glob("gpurun_out/tg_*.json")):
     print(f, "value %.1f e2e %.1f ms %.3f clocks %s" % (d["value"], d["e2e"]["value"], d["ms_per_step"], d["clocks"]["sm_mhz"]))
 PY
     ;;
-  *) echo "usage: $0 roles|timeline|halo|toggles"; exit 2 ;;
+  retune)  # re-measure the tile table for the bench batch and compare the bench under both tables, alternating
+    timeout 400 python tools/make_tile_table.py gpurun_out/b200_new.tsv 8 | tee gpurun_out/retune.txt
+    diff <(grep -v "^#" smap_b200/tiles/b200.tsv | grep " 8x" | sort) <(grep -v "^#" gpurun_out/b200_new.tsv | sort) | tee -a gpurun_out/retune.txt
+    b() { name=$1; shift; env "$@" timeout 300 python bench.py --steps 30 --warmup 5 --no-cpu-baseline > gpurun_out/rt_$name.json 2> gpurun_out/rt_$name.err; }
+    b old1 X=1; b new1 SMAPB_TILE_TABLE=$PWD/gpurun_out/b200_new.tsv; b old2 X=1; b new2 SMAPB_TILE_TABLE=$PWD/gpurun_out/b200_new.tsv
+    python - <<'PY' | tee -a gpurun_out/retune.txt
+import glob, json
+for f in sorted(glob.glob("gpurun_out/rt_*.json")):
+    d = json.loads(open(f).read().strip().splitlines()[-1])
+    print(f, "value %.1f e2e %.1f ms %.3f clocks %s" % (d["value"], d["e2e"]["value"], d["ms_per_step"], d["clocks"]["sm_mhz"]))
+PY
+    ;;
+  *) echo "usage: $0 roles|timeline|halo|toggles|retune"; exit 2 ;;
 esac
