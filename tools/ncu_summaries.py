@@ -24,8 +24,8 @@ for d in data:
     a[1] += v
     tot += v
 with open("profiles/%s_ncu_launch_list_summary.txt" % tag, "w") as f:
-    f.write("ncu --metrics gpu__time_duration.sum --clock-control none -s 1400 -c 460 python bench.py --steps 2 --warmup 3 (SMAPB_NO_GRAPH=1)\n")
-    f.write("%d consecutive launches; cold-cache serialised times: compare SHARES, not absolutes\n\n" % len(data))
+    f.write("SMAPB_NO_GRAPH=1 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none python bench.py --ncu-one-step --warmup 3 --engines 1\n")
+    f.write("%d launches = exactly one device-resident step of 8 frames; cold-cache serialised times: compare SHARES, not absolutes\n\n" % len(data))
     for k, (n, us) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         f.write("%-52s n=%4d  %9.1f us  %5.1f%%\n" % (k[:52], n, us, 100 * us / tot))
     conv = sum(us for k, (n, us) in agg.items() if "conv_tc" in k)
@@ -39,7 +39,7 @@ K = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
      "lts__t_sector_hit_rate.pct", "launch__registers_per_thread"]
 T = R = W = 0.0
 with open("profiles/%s_ncu_conv_tc_full_summary.txt" % tag, "w") as f:
-    f.write("ncu --set full --clock-control none --import-source on -k regex:conv_tc -s 230 -c 40 python bench.py --steps 1 --warmup 3\n")
+    f.write("SMAPB_NO_GRAPH=1 ncu --set full --clock-control none --import-source on -k regex:conv_tc -s 20 -c 10 python bench.py --ncu-one-step --warmup 3 --engines 1 (tools/gpu_final.sh)\n")
     f.write("%d consecutive conv_tc_kernel launches, B=8 832x512, bf16x3\n" % len(data))
     f.write("kernel                                        time_us  dram_rd_MB dram_wr_MB dram%  tensor_pipe%  l2_hit%  regs\n")
     for r in data:
