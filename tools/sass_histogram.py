@@ -21,7 +21,8 @@ for line in txt.splitlines():
     if m:
         total[m.group(1)] += 1
         per_kernel[cur][m.group(1).split(".")[0]] += 1
-KEYS = ("UTCHMMA", "LDTM", "UTMALDG", "UTMASTG", "UBLKCP", "UTCBAR", "UTCATOMSWS", "SYNCS", "UCGABAR", "FENCE", "HMMA", "IMMA")
+KEYS = ("UTCHMMA", "LDTM", "UTMALDG", "UTMASTG", "UBLKCP", "UTCBAR", "UTCATOMSWS", "SYNCS", "UCGABAR", "FENCE", "HMMA", "IMMA",
+        "FADD2", "FHADD", "FHFMA")  # the last three: packed fp32 / mixed bf16-fp32 arithmetic of the conv epilogue
 print("opcode histogram of smap_b200/lib/libsmap_b200.so (cuobjdump -sass, sm_100a)")
 for op, n in sorted(total.items(), key=lambda kv: -kv[1]):
     if op.startswith(KEYS):
