@@ -87,8 +87,8 @@ class ClockSampler(threading.Thread):
             # CUDA_VISIBLE_DEVICES may renumber the devices: address the GPU by the UUID torch reports
             import torch
 
-            uuid = str(torch.cuda.get_device_properties(gpu_index).uuid)
             try:
+                uuid = str(torch.cuda.get_device_properties(gpu_index).uuid)
                 self.handle = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
             except Exception:
                 self.handle = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
